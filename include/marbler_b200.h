@@ -1,0 +1,129 @@
+/* marbler_b200 -- C ABI of the batched MARBLER environment step on B200 (sm_100a).
+ *
+ * The reference (GT-STAR-Lab/MARBLER) is pure Python and has NO FFI of its own for this path; the
+ * only native boundary it crosses is cvxopt's CPython extension.  The entry points
+ * below are therefore the binding surface a maintainer would add (INTEGRATION.md shows the ctypes
+ * stub); each cites the reference interface it replaces.  Conventions: extern "C", plain pointers
+ * and sizes, no C++/torch types, no exceptions; 0 = ok, <0 = error (text via mrb_last_error).
+ * Stream-ordered: every call enqueues on the caller's CUDA stream and (except *_host) never
+ * synchronises.  The library never allocates caller-visible buffers: state / output buffers are
+ * device memory owned by the caller (PyTorch tensors) and handed over with mrb_bind.
+ * One handle per (process, GPU); a handle is not thread-safe (the reference is single-threaded).
+ */
+#ifndef MARBLER_B200_H
+#define MARBLER_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRB_ABI_VERSION 1
+#define MRB_MAX_ROBOTS 32
+#define MRB_MAX_PREY 32
+
+/* scenario ids: robotarium_gym/wrapper.py:12-16 env_dict, robotarium_gym/__init__.py:4-10 */
+enum { MRB_PCP = 0, MRB_WAREHOUSE = 1, MRB_MATERIAL = 2, MRB_ARCTIC = 3, MRB_SIMPLE = 4 };
+/* message codes: roboEnv.py:85-90 '' / 'collision' / 'boundary' / 'collision_boundary' */
+enum { MRB_MSG_NONE = 0, MRB_MSG_COLLISION = 1, MRB_MSG_BOUNDARY = 2, MRB_MSG_COLLISION_BOUNDARY = 3 };
+enum { MRB_OK = 0, MRB_E_ARG = -1, MRB_E_CUDA = -2, MRB_E_UNSUPPORTED = -3, MRB_E_STATE = -4 };
+
+/* grid spawn sampler = rps generate_initial_conditions + utilities/misc.py:49-63
+ * generate_initial_locations:  x = ((ix*spacing - w2) + sx1) + sx2,  y = ((iy*spacing - h2) + sy1) + sy2,
+ * (ix, iy) = divmod(cell, yr), `count` distinct cells of the xr*yr grid. */
+typedef struct mrb_spawn {
+    int32_t count, xr, yr, random_theta;
+    double spacing, w2, h2, sx1, sx2, sy1, sy2;
+} mrb_spawn;
+
+/* The scenario config.yaml keys the step path reads, already resolved. */
+typedef struct mrb_config {
+    int32_t struct_size;            /* sizeof(mrb_config), checked by mrb_create */
+    int32_t scenario;               /* MRB_PCP ... */
+    int32_t num_robots;             /* PCP: predator+capture (PredatorCapturePrey.py:19); else n_agents */
+    int32_t update_frequency;       /* roboEnv.py:52 */
+    int32_t ctrl_period;            /* 15, roboEnv.py:63 */
+    int32_t robotarium;             /* roboEnv.py:63: controller every sub-step */
+    int32_t penalize_violations;    /* roboEnv.py:82 */
+    int32_t barrier_default;        /* 0 'safe' (certificate2, r=.2), 1 'default' (r=.17): controller.py:13-16 */
+    int32_t max_episode_steps;
+    int32_t num_neighbors;          /* PCP / Warehouse */
+    int32_t capability_aware;       /* PCP / MaterialTransport */
+    int32_t num_prey, num_predators;                 /* PCP */
+    int32_t n_fast, small_torque, large_torque;      /* MaterialTransport */
+    int32_t auto_reset;             /* re-sample finished envs at the end of mrb_step */
+    int32_t track_dist;             /* info['dist_travelled'] (roboEnv.py:55-56,93) */
+    int32_t collect_stats;          /* episode statistics vector, see mrb_buffers.stats */
+    int32_t reserved0;
+    double left, right, up, down;   /* LEFT/RIGHT/UP/DOWN */
+    double step_dist;               /* step_dist; ArcticTransport normal_step */
+    double fast_step, slow_step;    /* MaterialTransport / ArcticTransport */
+    double predator_radius, capture_radius;
+    double time_penalty, sense_reward, capture_reward;
+    double load_reward, unload_reward, goal_width;   /* Warehouse; MT: load/unload multiplier, end_goal_width */
+    double zone1_radius;
+    double not_reached_penalty, dist_multiplier;     /* ArcticTransport */
+    double reward_scaler;                            /* Simple */
+    double violation_reward;        /* -5 / -5 / -6 / -30 / -5 (literals in each scenario's step()) */
+    double zone_mu[2], zone_sigma[2];                /* MaterialTransport zone1/zone2 normal(loc, scale) */
+    mrb_spawn spawn_robots, spawn_other;             /* robots; PCP prey / Simple goal */
+} mrb_config;
+
+/* Caller-owned device buffers.  State is structure-of-arrays with the env index fastest:
+ *   state_f64[row][env], state_i32[row][env]   (row counts from mrb_state_rows; rows named in
+ *   marbler_b200/layout.py and DESIGN.md).  Outputs:
+ *   obs f32 [B][N][D] | reward f32 [B][N] | done u8 [B] | message u8 [B] | remaining i32 [B] |
+ *   dist f32 [B][N] (may be NULL when track_dist == 0) | stats f64 [MRB_NUM_STATS] (may be NULL). */
+#define MRB_NUM_STATS 16
+enum { MRB_STAT_EPISODES = 0, MRB_STAT_RETURN = 1, MRB_STAT_LENGTH = 2, MRB_STAT_COLLISION = 3,
+       MRB_STAT_BOUNDARY = 4, MRB_STAT_SCENARIO = 5, MRB_STAT_ENV_STEPS = 6, MRB_STAT_QP_SOLVES = 7,
+       MRB_STAT_QP_ITERS = 8, MRB_STAT_TIMEOUTS = 9 };
+typedef struct mrb_buffers {
+    double *state_f64;
+    int32_t *state_i32;
+    float *obs;
+    float *reward;
+    uint8_t *done;
+    uint8_t *message;
+    int32_t *remaining;
+    float *dist;
+    double *stats;
+} mrb_buffers;
+
+typedef struct mrb_env mrb_env;
+
+int mrb_version(void);
+/* replaces Wrapper.__init__ -> env_dict[env_name](args) (wrapper.py:20-34): builds the handle for
+ * num_envs independent envs whose global ids are env_id0 .. env_id0+num_envs-1 (RNG stream offset
+ * of this rank when envs are sharded over GPUs). */
+int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, int64_t env_id0, mrb_env **out);
+int mrb_destroy(mrb_env *env);
+const char *mrb_last_error(const mrb_env *env);          /* env may be NULL: last create error */
+/* layout queries (spaces: <Scenario>.get_observation_space / get_action_space) */
+int mrb_state_rows(const mrb_env *env, int32_t *rows_f64, int32_t *rows_i32);
+int mrb_obs_dim(const mrb_env *env);
+int mrb_num_actions(const mrb_env *env);
+int mrb_bind(mrb_env *env, const mrb_buffers *buffers);
+/* replaces <Scenario>.reset() + roboEnv.reset() (e.g. PredatorCapturePrey.py:114-136,
+ * roboEnv.py:27-36,98-118).  mask: device u8[B] (NULL = all envs).  Zeroes obs of the reset envs
+ * (the reference returns an all-zero observation from reset). */
+int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void *cuda_stream);
+/* replaces Wrapper.step(action_n) (wrapper.py:41-44) -> <Scenario>.step -> roboEnv.step
+ * (roboEnv.py:38-96) -> Controller.set_velocities (controller.py:20-25) -> rps / cvxopt.
+ * actions: device i32 [B][N]. */
+int mrb_step(mrb_env *env, const int32_t *actions, void *cuda_stream);
+/* same step with HOST buffers (pinned or pageable): H2D actions, step, D2H obs/reward/done/message,
+ * then synchronises the stream.  NULL host outputs are skipped. */
+int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
+                  uint8_t *done_host, uint8_t *message_host, void *cuda_stream);
+/* unit entry for the barrier-certificate QP alone (rps create_single_integrator_barrier_certificate{,2}
+ * -> cvxopt.solvers.qp; called at controller.py:23).  Device SoA: dxi, xi, u are f64 [2][N][B];
+ * iters i32 [B] (may be NULL). */
+int mrb_barrier_qp(int device, int32_t num_robots, int32_t barrier_default, int64_t num_problems,
+                   const double *dxi, const double *xi, double *u, int32_t *iters, void *cuda_stream);
+/* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
+int64_t mrb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,302 @@
+// C ABI of libmarbler_b200.so (see include/marbler_b200.h).  Host side only validates, fills the
+// kernel parameter block and launches; all arithmetic is in the kernels.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "step_thread.cuh"
+#include "step_warp.cuh"
+
+using namespace mrb;
+
+struct mrb_env {
+    Params p;
+    int device;
+    bool bound;
+    int32_t *actions_dev;       // staging for mrb_step_host
+    std::string err;
+};
+
+static std::string g_create_error;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(mrb_env *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+static int cuda_fail(mrb_env *e, cudaError_t st, const char *what)
+{
+    return fail(e, MRB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(st));
+}
+
+// largest t with fl(sqrt(t)) <= r: sqrt(d2) <= r  <=>  d2 <= t for every double d2 >= 0
+static double thr2(double r)
+{
+    if (!(r > 0.0)) return 0.0;
+    double t = r * r;
+    while (std::sqrt(t) > r) t = std::nextafter(t, 0.0);
+    while (std::sqrt(std::nextafter(t, INFINITY)) <= r) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
+static int obs_block_count(const mrb_config &c)
+{
+    const int others = c.num_robots - 1;
+    return 1 + (c.num_neighbors >= others ? others : c.num_neighbors);
+}
+static int obs_dim_of(const mrb_config &c)
+{
+    switch (c.scenario) {
+    case MRB_PCP: return (c.capability_aware ? 6 : 4) * obs_block_count(c);       // PredatorCapturePrey.py:30-33,52
+    case MRB_WAREHOUSE: return 3 * obs_block_count(c);                             // warehouse.py:52,70
+    case MRB_MATERIAL: return c.capability_aware ? 11 : 9;                         // MaterialTransport.py:55-58
+    case MRB_ARCTIC: return 30;                                                    // ArcticTransport.py:19
+    default: return 2 * (c.num_robots + 1);                                        // simple.py:98
+    }
+}
+
+extern "C" int mrb_version(void) { return MRB_ABI_VERSION; }
+extern "C" int64_t mrb_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char *mrb_last_error(const mrb_env *env) { return env ? env->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, int64_t env_id0, mrb_env **out)
+{
+    if (!cfg || !out) return fail(nullptr, MRB_E_ARG, "mrb_create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(mrb_config))
+        return fail(nullptr, MRB_E_ARG, "mrb_create: mrb_config.struct_size does not match this library (ABI mismatch)");
+    const mrb_config &c = *cfg;
+    if (c.scenario < MRB_PCP || c.scenario > MRB_SIMPLE) return fail(nullptr, MRB_E_ARG, "mrb_create: unknown scenario");
+    if (c.num_robots < 1 || c.num_robots > MRB_MAX_ROBOTS) return fail(nullptr, MRB_E_ARG, "mrb_create: num_robots must be in [1, 32]");
+    if (num_envs < 1) return fail(nullptr, MRB_E_ARG, "mrb_create: num_envs must be >= 1");
+    if (c.update_frequency < 1 || c.ctrl_period < 1) return fail(nullptr, MRB_E_ARG, "mrb_create: update_frequency / ctrl_period must be >= 1");
+    if (c.scenario == MRB_PCP && (c.num_prey < 1 || c.num_prey > MRB_MAX_PREY || c.num_predators < 0 || c.num_predators > c.num_robots))
+        return fail(nullptr, MRB_E_ARG, "mrb_create: PredatorCapturePrey needs 1..32 prey and predators <= robots");
+    if (c.scenario == MRB_ARCTIC && c.num_robots != 4)
+        return fail(nullptr, MRB_E_ARG, "mrb_create: ArcticTransport is defined for exactly 4 robots (ArcticTransport.py:25-33)");
+    if (c.scenario == MRB_MATERIAL && c.num_robots < 4)
+        return fail(nullptr, MRB_E_ARG, "mrb_create: MaterialTransport reads 4 messages (MaterialTransport.py:119-120)");
+    if ((c.scenario == MRB_PCP || c.scenario == MRB_WAREHOUSE) && c.num_neighbors < 0)
+        return fail(nullptr, MRB_E_ARG, "mrb_create: num_neighbors must be >= 0");
+    if (c.scenario != MRB_ARCTIC) {
+        const mrb_spawn &s = c.spawn_robots;
+        if (s.count != c.num_robots || s.xr * s.yr <= s.count || s.xr * s.yr > 64)
+            return fail(nullptr, MRB_E_ARG, "mrb_create: robot spawn grid must have more cells than robots (rps assert) and at most 64");
+    }
+    if (c.scenario == MRB_PCP || c.scenario == MRB_SIMPLE) {
+        const mrb_spawn &s = c.spawn_other;
+        const int want = c.scenario == MRB_PCP ? c.num_prey : 1;
+        if (s.count != want || s.xr * s.yr <= s.count || s.xr * s.yr > 64)
+            return fail(nullptr, MRB_E_ARG, "mrb_create: prey/goal spawn grid must have more cells than items and at most 64");
+    }
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        return fail(nullptr, MRB_E_CUDA, "mrb_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, MRB_E_ARG, "mrb_create: bad device index");
+    cudaDeviceProp prop;
+    if ((st = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, st, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, MRB_E_UNSUPPORTED, "mrb_create: kernels are built for sm_100a (B200) only");
+
+    mrb_env *e = new (std::nothrow) mrb_env();
+    if (!e) return fail(nullptr, MRB_E_ARG, "mrb_create: out of host memory");
+    std::memset(&e->p, 0, sizeof(Params));
+    e->p.cfg = c;
+    e->p.B = num_envs;
+    e->p.env_id0 = env_id0;
+    e->p.seed = 0;
+    e->p.obs_dim = obs_dim_of(c);
+    e->p.obs_blocks = obs_block_count(c);
+    e->p.rows_f64 = rows_f64(c);
+    e->p.rows_i32 = rows_i32(c);
+    e->p.collision_thr2 = thr2(kCollisionDiameter);
+    e->p.sense_thr2 = thr2(c.predator_radius);
+    e->p.capture_thr2 = thr2(c.capture_radius);
+    e->p.zone1_thr2 = thr2(c.zone1_radius);
+    e->device = device;
+    e->bound = false;
+    e->actions_dev = nullptr;
+    *out = e;
+    return MRB_OK;
+}
+
+extern "C" int mrb_destroy(mrb_env *env)
+{
+    if (!env) return MRB_E_ARG;
+    if (env->actions_dev) { cudaSetDevice(env->device); cudaFree(env->actions_dev); }
+    delete env;
+    return MRB_OK;
+}
+
+extern "C" int mrb_state_rows(const mrb_env *env, int32_t *rf, int32_t *ri)
+{
+    if (!env || !rf || !ri) return MRB_E_ARG;
+    *rf = env->p.rows_f64; *ri = env->p.rows_i32;
+    return MRB_OK;
+}
+extern "C" int mrb_obs_dim(const mrb_env *env) { return env ? env->p.obs_dim : MRB_E_ARG; }
+extern "C" int mrb_num_actions(const mrb_env *env)
+{
+    if (!env) return MRB_E_ARG;
+    return env->p.cfg.scenario == MRB_MATERIAL ? 20 : 5;     // spaces.Discrete(20) MaterialTransport.py:80, Discrete(5) elsewhere
+}
+
+extern "C" int mrb_bind(mrb_env *env, const mrb_buffers *b)
+{
+    if (!env || !b) return MRB_E_ARG;
+    if (!b->state_f64 || !b->state_i32 || !b->obs || !b->reward || !b->done || !b->message || !b->remaining)
+        return fail(env, MRB_E_ARG, "mrb_bind: state_f64, state_i32, obs, reward, done, message, remaining are required");
+    if (env->p.cfg.track_dist && !b->dist) return fail(env, MRB_E_ARG, "mrb_bind: track_dist set but dist buffer is NULL");
+    if (((uintptr_t)b->state_f64 | (uintptr_t)b->obs | (uintptr_t)b->reward) & 15)
+        return fail(env, MRB_E_ARG, "mrb_bind: buffers must be 16-byte aligned");
+    env->p.buf = *b;
+    env->bound = true;
+    return MRB_OK;
+}
+
+template <int SCN>
+static void launch_reset(mrb_env *e, const uint8_t *mask, cudaStream_t s)
+{
+    const int tpb = 128;
+    reset_kernel<SCN><<<(unsigned)((e->p.B + tpb - 1) / tpb), tpb, 0, s>>>(e->p, mask);
+    g_launches++;
+}
+
+extern "C" int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void *stream)
+{
+    if (!env) return MRB_E_ARG;
+    if (!env->bound) return fail(env, MRB_E_STATE, "mrb_reset: call mrb_bind first");
+    cudaError_t st = cudaSetDevice(env->device);
+    if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
+    env->p.seed = seed;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (env->p.cfg.scenario) {
+    case MRB_PCP: launch_reset<MRB_PCP>(env, mask, s); break;
+    case MRB_WAREHOUSE: launch_reset<MRB_WAREHOUSE>(env, mask, s); break;
+    case MRB_MATERIAL: launch_reset<MRB_MATERIAL>(env, mask, s); break;
+    case MRB_ARCTIC: launch_reset<MRB_ARCTIC>(env, mask, s); break;
+    default: launch_reset<MRB_SIMPLE>(env, mask, s); break;
+    }
+    if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(env, st, "reset kernel launch");
+    return MRB_OK;
+}
+
+template <int SCN, int N>
+static void launch_thread(mrb_env *e, const int32_t *actions, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((e->p.B + kThreadsPerBlock - 1) / kThreadsPerBlock);
+    step_thread_kernel<SCN, N><<<grid, kThreadsPerBlock, 0, s>>>(e->p, actions);
+    g_launches++;
+}
+template <int SCN>
+static void launch_warp(mrb_env *e, const int32_t *actions, cudaStream_t s)
+{
+    launch_step_warp<SCN>(e->p, actions, s);
+    g_launches++;
+}
+
+template <int SCN>
+static int dispatch_step(mrb_env *e, const int32_t *actions, cudaStream_t s)
+{
+    switch (e->p.cfg.num_robots) {
+    case 4: launch_thread<SCN, 4>(e, actions, s); return MRB_OK;
+    default: break;
+    }
+    if (SCN == MRB_ARCTIC) return MRB_E_UNSUPPORTED;
+    launch_warp<SCN>(e, actions, s);
+    return MRB_OK;
+}
+
+extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
+{
+    if (!env || !actions) return MRB_E_ARG;
+    if (!env->bound) return fail(env, MRB_E_STATE, "mrb_step: call mrb_bind first");
+    if ((uintptr_t)actions & 15) return fail(env, MRB_E_ARG, "mrb_step: actions must be 16-byte aligned");
+    cudaError_t st = cudaSetDevice(env->device);
+    if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    switch (env->p.cfg.scenario) {
+    case MRB_PCP: rc = dispatch_step<MRB_PCP>(env, actions, s); break;
+    case MRB_WAREHOUSE: rc = dispatch_step<MRB_WAREHOUSE>(env, actions, s); break;
+    case MRB_MATERIAL: rc = dispatch_step<MRB_MATERIAL>(env, actions, s); break;
+    case MRB_ARCTIC: rc = dispatch_step<MRB_ARCTIC>(env, actions, s); break;
+    default: rc = dispatch_step<MRB_SIMPLE>(env, actions, s); break;
+    }
+    if (rc != MRB_OK) return fail(env, rc, "mrb_step: no kernel for this (scenario, num_robots)");
+    if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(env, st, "step kernel launch");
+    return MRB_OK;
+}
+
+extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
+                             uint8_t *done_host, uint8_t *message_host, void *stream)
+{
+    if (!env || !actions_host) return MRB_E_ARG;
+    if (!env->bound) return fail(env, MRB_E_STATE, "mrb_step_host: call mrb_bind first");
+    cudaError_t st = cudaSetDevice(env->device);
+    if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t B = env->p.B, N = env->p.cfg.num_robots, D = env->p.obs_dim;
+    if (!env->actions_dev && (st = cudaMalloc(&env->actions_dev, sizeof(int32_t) * B * N)) != cudaSuccess)
+        return cuda_fail(env, st, "cudaMalloc(actions staging)");
+    if ((st = cudaMemcpyAsync(env->actions_dev, actions_host, sizeof(int32_t) * B * N, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        return cuda_fail(env, st, "H2D actions");
+    const int rc = mrb_step(env, env->actions_dev, stream);
+    if (rc != MRB_OK) return rc;
+    const mrb_buffers &b = env->p.buf;
+    if (obs_host && (st = cudaMemcpyAsync(obs_host, b.obs, sizeof(float) * B * N * D, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(env, st, "D2H obs");
+    if (reward_host && (st = cudaMemcpyAsync(reward_host, b.reward, sizeof(float) * B * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(env, st, "D2H reward");
+    if (done_host && (st = cudaMemcpyAsync(done_host, b.done, (size_t)B, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(env, st, "D2H done");
+    if (message_host && (st = cudaMemcpyAsync(message_host, b.message, (size_t)B, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(env, st, "D2H message");
+    if ((st = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(env, st, "mrb_step_host sync");
+    return MRB_OK;
+}
+
+// ---- barrier QP alone
+template <int N>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+qp_thread_kernel(int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
+                 double *__restrict__ u, int32_t *__restrict__ iters)
+{
+    const int64_t e = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
+    if (e >= B) return;
+    double xix[N], xiy[N], ux[N], uy[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        xix[i] = xi[i * B + e]; xiy[i] = xi[(N + i) * B + e];
+        ux[i] = dxi[i * B + e]; uy[i] = dxi[(N + i) * B + e];
+    }
+    QpThread<N> qp;
+    const int it = qp.run(xix, xiy, ux, uy, barrier_default != 0);
+#pragma unroll
+    for (int i = 0; i < N; i++) { u[i * B + e] = ux[i]; u[(N + i) * B + e] = uy[i]; }
+    if (iters) iters[e] = it;
+}
+
+extern "C" int mrb_barrier_qp(int device, int32_t N, int32_t barrier_default, int64_t B, const double *dxi,
+                              const double *xi, double *u, int32_t *iters, void *stream)
+{
+    if (!dxi || !xi || !u || B < 1 || N < 1 || N > MRB_MAX_ROBOTS) return fail(nullptr, MRB_E_ARG, "mrb_barrier_qp: bad argument");
+    cudaError_t st = cudaSetDevice(device);
+    if (st != cudaSuccess) return cuda_fail(nullptr, st, "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock);
+    switch (N) {
+    case 2: qp_thread_kernel<2><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
+    case 3: qp_thread_kernel<3><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
+    case 4: qp_thread_kernel<4><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
+    default: launch_qp_warp(N, barrier_default, B, dxi, xi, u, iters, s); break;
+    }
+    g_launches++;
+    if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(nullptr, st, "qp kernel launch");
+    return MRB_OK;
+}

@@ -1,0 +1,106 @@
+// Shared device-side definitions for the marbler_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/marbler_b200.h"
+
+namespace mrb {
+
+// rps RobotariumABC constants -- the ones flagged "(?)" there are named here
+// so that a correction against rps@6bb184e is a one-line change.
+constexpr double kTimeStep = 0.033;
+constexpr double kMaxLinearVelocity = 0.2;
+constexpr double kMaxAngularVelocity = 2.0 * (0.016 / 0.11) * (0.2 / 0.016);
+constexpr double kCollisionDiameter = 0.135;
+constexpr double kArenaXMin = -1.6, kArenaXMax = -1.6 + 3.2, kArenaYMin = -1.0, kArenaYMax = -1.0 + 2.0;
+// controller constants (App. A.6 - A.8)
+constexpr double kProjectionDistance = 0.05;
+constexpr double kSiVelocityLimit = 0.15;
+constexpr double kAngularLimit = 3.14159265358979323846;
+constexpr double kQpMagnitudeLimit = 0.2;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+
+// Everything a kernel needs, passed by value (__grid_constant__).
+struct Params {
+    mrb_config cfg;
+    mrb_buffers buf;
+    int64_t B;          // envs on this device
+    int64_t env_id0;    // global id of env 0 (RNG stream offset of this rank)
+    uint64_t seed;
+    int32_t obs_dim;    // D
+    int32_t obs_blocks; // neighbour blocks per agent incl. self (PCP / Warehouse)
+    int32_t rows_f64, rows_i32;
+    // exact squared thresholds: sqrt(d2) <= r  <=>  d2 <= thr2(r)   (computed on the host)
+    double collision_thr2, sense_thr2, capture_thr2, zone1_thr2;
+};
+
+// ---- state rows (env index fastest).  f64 rows:
+//   [0,N) x | [N,2N) y | [2N,3N) theta | [3N,4N) prev x | [4N,5N) prev y | 5N: episode return |
+//   5N+1 ..: scenario rows (PCP prey x0,y0,x1,y1,...; Simple goal x,y)
+// i32 rows: 0 episode_steps | 1 prev_valid | 2 episode_count | 3.. scenario rows
+//   PCP: sensed mask, captured mask | Warehouse: loaded mask |
+//   MaterialTransport: load[N], zone1, zone2, messages (2 bits each) |
+//   ArcticTransport: grid (6 words, 2 bits per cell, cell = row*12+col), goal_col, pixel_type (2 bits each), reached mask
+__host__ __device__ inline int scenario_rows_f64(const mrb_config &c)
+{
+    return c.scenario == MRB_PCP ? 2 * c.num_prey : (c.scenario == MRB_SIMPLE ? 2 : 0);
+}
+__host__ __device__ inline int scenario_rows_i32(const mrb_config &c)
+{
+    switch (c.scenario) {
+    case MRB_PCP: return 2;
+    case MRB_WAREHOUSE: return 1;
+    case MRB_MATERIAL: return c.num_robots + 3;
+    case MRB_ARCTIC: return 9;
+    default: return 0;
+    }
+}
+__host__ __device__ inline int rows_f64(const mrb_config &c) { return 5 * c.num_robots + 1 + scenario_rows_f64(c); }
+__host__ __device__ inline int rows_i32(const mrb_config &c) { return 3 + scenario_rows_i32(c); }
+
+// ---- Philox4x32-10 (Salmon et al. SC'11); key = seed, counter = (env id, episode, block)
+struct Philox {
+    uint32_t key0, key1, c0, c1, c2, c3, buf[4];
+    int have;
+    __device__ Philox(uint64_t seed, uint64_t env_id, uint32_t episode)
+        : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)), c0((uint32_t)env_id), c1((uint32_t)(env_id >> 32)),
+          c2(episode), c3(0), have(0) {}
+    __device__ void refill()
+    {
+        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, a0), lo0 = 0xD2511F53u * a0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, a2), lo1 = 0xCD9E8D57u * a2;
+            uint32_t n0 = hi1 ^ a1 ^ k0, n2 = hi0 ^ a3 ^ k1;
+            a0 = n0; a1 = lo1; a2 = n2; a3 = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        buf[0] = a0; buf[1] = a1; buf[2] = a2; buf[3] = a3;
+        c3++;
+        have = 4;
+    }
+    __device__ uint32_t u32()
+    {
+        if (!have) refill();
+        uint32_t v = have == 4 ? buf[0] : (have == 3 ? buf[1] : (have == 2 ? buf[2] : buf[3]));
+        have--;
+        return v;
+    }
+    __device__ uint32_t below(uint32_t n) { return __umulhi(u32(), n); }
+    __device__ double unit()
+    {
+        uint32_t a = u32() >> 5, b = u32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+    __device__ double normal()
+    {
+        double u1 = 1.0 - unit(), u2 = unit();
+        return sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);
+    }
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+}  // namespace mrb

@@ -1,0 +1,583 @@
+// One environment per thread: the whole MARBLER env step (goal generation, UF sub-steps of
+// controller + barrier QP + unicycle integration + violation checks, scenario events / observations
+// / rewards / done, optional auto-reset) between one coalesced read and one write of the SoA state.
+//
+// Reference call stack being replaced:
+//   wrapper.py:41-44 Wrapper.step -> <Scenario>.step -> utilities/roboEnv.py:38-96 roboEnv.step
+//   -> utilities/controller.py:20-25 -> rps (App. A.2-A.8) -> cvxopt.solvers.qp (A.9)
+#pragma once
+#include "common.cuh"
+#include "qp_thread.cuh"
+
+namespace mrb {
+
+constexpr int kThreadsPerBlock = 64;
+
+// every scenario's Agent.generate_goal: PredatorCapturePrey/agent.py:48-76, warehouse.py:19-45,
+// MaterialTransport.py:19-46, ArcticTransport/agent.py:114-137, simple.py:32-60
+__device__ __forceinline__ void generate_goal(const mrb_config &c, double step, int action, double x, double y,
+                                              double &gx, double &gy)
+{
+    const double cx = x < c.left ? c.left : (x > c.right ? c.right : x);
+    const double cy = y < c.up ? c.up : (y > c.down ? c.down : y);
+    gx = cx; gy = cy;
+    if (action == 0) gx = fmax(x - step, c.left);
+    else if (action == 1) gx = fmin(x + step, c.right);
+    else if (action == 2) gy = fmax(y - step, c.up);
+    else if (action == 3) gy = fmin(y + step, c.down);
+}
+
+template <int SCN, int N>
+__device__ __forceinline__ double agent_step_size(const mrb_config &c, int i, int pixel_types)
+{
+    if (SCN == MRB_MATERIAL) return i < c.n_fast ? c.fast_step : c.slow_step;       // MaterialTransport.py:71-74
+    if (SCN == MRB_ARCTIC) {                                                          // ArcticTransport/agent.py:94-112
+        if (i < 2) return c.fast_step;
+        const int p = (pixel_types >> (2 * i)) & 3;
+        if (i == 3) return p == 1 ? c.slow_step : (p == 2 ? c.fast_step : c.step_dist);
+        return p == 1 ? c.fast_step : (p == 2 ? c.slow_step : c.step_dist);
+    }
+    return c.step_dist;
+}
+
+// ArcticTransport.py:136-143 get_cell_from_pose (int() truncates toward zero)
+__device__ __forceinline__ void arctic_cell(double x, double y, int &row, int &col)
+{
+    int r = -(int)((y - 1.0) / .25), cc = (int)((x + 1.5) / .25);
+    row = r < 0 ? 0 : (r > 7 ? 7 : r);
+    col = cc < 0 ? 0 : (cc > 11 ? 11 : cc);
+}
+__device__ __forceinline__ int arctic_grid(const uint32_t (&g)[6], int row, int col)
+{
+    const int k = row * 12 + col, wi = k >> 4;
+    uint32_t w = g[0];
+#pragma unroll
+    for (int t = 1; t < 6; t++) w = (wi == t) ? g[t] : w;
+    return (w >> (2 * (k & 15))) & 3;
+}
+
+// ---- reset: <Scenario>.reset() + roboEnv.reset() (distributional parity)
+// N distinct cells of the spawn grid, uniformly, in order (rps generate_initial_conditions, App. A.5)
+template <typename F>
+__device__ __forceinline__ void spawn_grid(const mrb_spawn &sp, Philox &g, F emit)
+{
+    uint64_t taken = 0;
+    const int cells = sp.xr * sp.yr;
+    for (int i = 0; i < sp.count; i++) {
+        int r = (int)g.below((uint32_t)(cells - i)), cell = 0;
+        for (; cell < cells; cell++) {
+            if ((taken >> cell) & 1) continue;
+            if (r-- == 0) break;
+        }
+        taken |= 1ull << cell;
+        const int ix = cell / sp.yr, iy = cell % sp.yr;
+        const double x = ((ix * sp.spacing - sp.w2) + sp.sx1) + sp.sx2;
+        const double y = ((iy * sp.spacing - sp.h2) + sp.sy1) + sp.sy2;
+        double th = 0.0;
+        if (sp.random_theta) {                       // warehouse.py:93 keeps rps' random heading
+            th = g.unit() * kTwoPi - kPi;
+            th = atan2(sin(th), cos(th));            // the zero-velocity sim step of roboEnv.py:112
+        }
+        emit(i, x, y, th);
+    }
+}
+
+template <int SCN>
+__device__ void reset_env(const Params &p, int64_t env)
+{
+    const mrb_config &c = p.cfg;
+    const int N = c.num_robots;
+    const int64_t S = p.B;
+    double *sf = p.buf.state_f64 + env;
+    int32_t *si = p.buf.state_i32 + env;
+    Philox g(p.seed, (uint64_t)(p.env_id0 + env), (uint32_t)si[2 * S]);
+    si[0] = 0;
+    si[1 * S] = 0;
+    si[2 * S] += 1;
+    for (int r = 3 * N; r < 5 * N + 1; r++) sf[r * S] = 0.0;       // prev pose, episode return
+    int32_t *sci = si + 3 * S;
+    double *scf = sf + (5 * N + 1) * S;
+    if (SCN == MRB_ARCTIC) {                                        // ArcticTransport.py:28-33, 56-82
+        const double sx[4] = {-.3, .3, -.9, .9};
+        for (int i = 0; i < N; i++) {
+            sf[i * S] = sx[i & 3];
+            sf[(N + i) * S] = -.8;
+            sf[(2 * N + i) * S] = atan2(sin(kPi / 2), cos(kPi / 2));
+        }
+        uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 96; k++) w[k >> 4] |= g.below(3) << (2 * (k & 15));
+        const int gc = 1 + (int)g.below(11);
+        for (int k = 1; k < 11; k++) w[(84 + k) >> 4] &= ~(3u << (2 * ((84 + k) & 15)));
+        const int goal_cells[4] = {gc, gc - 1, 12 + gc, 12 + gc - 1};
+        for (int t = 0; t < 4; t++) w[goal_cells[t] >> 4] |= 3u << (2 * (goal_cells[t] & 15));
+        for (int t = 0; t < 6; t++) sci[t * S] = (int32_t)w[t];
+        sci[6 * S] = gc;
+        sci[7 * S] = 0;
+        sci[8 * S] = 0;
+        return;
+    }
+    spawn_grid(c.spawn_robots, g, [&](int i, double x, double y, double th) {
+        sf[i * S] = x; sf[(N + i) * S] = y; sf[(2 * N + i) * S] = th;
+    });
+    if (SCN == MRB_PCP) {                                           // PredatorCapturePrey.py:128-132
+        spawn_grid(c.spawn_other, g, [&](int i, double x, double y, double) {
+            scf[(2 * i) * S] = x; scf[(2 * i + 1) * S] = y;
+        });
+        sci[0] = 0; sci[S] = 0;
+    } else if (SCN == MRB_SIMPLE) {                                 // simple.py:141-144
+        spawn_grid(c.spawn_other, g, [&](int, double x, double y, double) { scf[0] = x; scf[S] = y; });
+    } else if (SCN == MRB_WAREHOUSE) {
+        sci[0] = 0;
+    } else if (SCN == MRB_MATERIAL) {                               // MaterialTransport.py:96-103
+        for (int i = 0; i < N; i++) sci[i * S] = 0;
+        for (int k = 0; k < 2; k++) sci[(N + k) * S] = (int32_t)(c.zone_mu[k] + c.zone_sigma[k] * g.normal());
+        sci[(N + 2) * S] = 0;
+    }
+}
+
+template <int SCN>
+__global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *mask)
+{
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.B) return;
+    if (mask && !mask[env]) return;
+    reset_env<SCN>(p, env);
+    // the reference returns an all-zero observation from reset (e.g. PredatorCapturePrey.py:136)
+    const int nd = p.cfg.num_robots * p.obs_dim;
+    float *o = p.buf.obs + env * nd;
+    for (int k = 0; k < nd; k++) o[k] = 0.f;
+}
+
+// ---- the step
+template <int SCN, int N>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
+{
+    const int64_t env = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
+    if (env >= p.B) return;
+    const mrb_config &c = p.cfg;
+    const int64_t S = p.B;
+    double *sf = p.buf.state_f64 + env;
+    int32_t *si = p.buf.state_i32 + env;
+    int32_t *sci = si + 3 * S;
+    double *scf = sf + (5 * N + 1) * S;
+
+    double px[N], py[N], th[N], qx[N], qy[N];
+    int act[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        px[i] = sf[i * S]; py[i] = sf[(N + i) * S]; th[i] = sf[(2 * N + i) * S];
+        qx[i] = sf[(3 * N + i) * S]; qy[i] = sf[(4 * N + i) * S];
+    }
+    if (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const int4 a = *reinterpret_cast<const int4 *>(actions + env * N + i);
+            act[i] = a.x; act[i + 1] = a.y; act[i + 2] = a.z; act[i + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) act[i] = actions[env * N + i];
+    }
+    const int steps = si[0] + 1;                  // episode_steps += 1: first line of every step()
+    const bool prev_valid = si[S] != 0;
+    int at_pix = 0, at_reached = 0;
+    if (SCN == MRB_ARCTIC) { at_pix = sci[7 * S]; at_reached = sci[8 * S]; }
+
+    // roboEnv.py:42 -> _generate_step_goal_positions: goals from the pose at entry
+    double gx[N], gy[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int a = SCN == MRB_MATERIAL ? act[i] / 4 : act[i];           // MaterialTransport.py:23
+        generate_goal(c, agent_step_size<SCN, N>(c, i, at_pix), a, px[i], py[i], gx[i], gy[i]);
+    }
+
+    double v[N], om[N], cs[N], sn[N], cd[N], sd[N], dist[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { v[i] = 0.0; om[i] = 0.0; cs[i] = 1.0; sn[i] = 0.0; cd[i] = 1.0; sd[i] = 0.0; dist[i] = 0.0; }
+    if (c.track_dist && prev_valid) {             // roboEnv.py:55-56 at sub-step 0
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const double dx = px[i] - qx[i], dy = py[i] - qy[i];
+            dist[i] = sqrt(dx * dx + dy * dy);
+        }
+    }
+    int msg = 0, n_qp = 0, n_it = 0;
+    const int UF = c.update_frequency;
+    for (int k = 0; k < UF; k++) {                // roboEnv.py:52
+        // :55-56 for k >= 1: |pose_k - pose_{k-1}| = dt |v_{k-1}| (c^2 + s^2 = 1)
+        if (k > 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) dist[i] += kTimeStep * fabs(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) { qx[i] = px[i]; qy[i] = py[i]; }      // :59
+        if (k % c.ctrl_period == 0 || c.robotarium) {                       // :63-65
+            double xix[N], xiy[N], ux[N], uy[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                sincos(th[i], &sn[i], &cs[i]);
+                xix[i] = px[i] + kProjectionDistance * cs[i];              // uni_to_si_states (A.7)
+                xiy[i] = py[i] + kProjectionDistance * sn[i];
+                double dx = gx[i] - xix[i], dy = gy[i] - xiy[i];           // si_position_controller (A.6)
+                const double nrm = sqrt(dx * dx + dy * dy);
+                if (nrm > kSiVelocityLimit) {
+                    const double sc = kSiVelocityLimit / nrm;
+                    dx *= sc; dy *= sc;
+                }
+                ux[i] = dx; uy[i] = dy;
+            }
+            QpThread<N> qp;
+            n_it += qp.run(xix, xiy, ux, uy, c.barrier_default != 0);      // controller.py:23
+            n_qp++;
+#pragma unroll
+            for (int i = 0; i < N; i++) {                                   // si_to_uni_dyn (A.7) + saturation (A.2)
+                double vv = cs[i] * ux[i] + sn[i] * uy[i];
+                double ww = (1.0 / kProjectionDistance) * (-sn[i] * ux[i] + cs[i] * uy[i]);
+                ww = clampd(ww, -kAngularLimit, kAngularLimit);
+                v[i] = clampd(vv, -kMaxLinearVelocity, kMaxLinearVelocity);
+                om[i] = clampd(ww, -kMaxAngularVelocity, kMaxAngularVelocity);
+                sincos(kTimeStep * om[i], &sd[i], &cd[i]);
+            }
+        }
+        // Robotarium.step (A.3): _validate (A.4) on the entering pose, then Euler update in place
+        bool viol_b = false, viol_c = false;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            viol_b |= (px[i] < kArenaXMin) | (px[i] > kArenaXMax) | (py[i] < kArenaYMin) | (py[i] > kArenaYMax);
+#pragma unroll
+        for (int i = 0; i < N - 1; i++)
+#pragma unroll
+            for (int j = i + 1; j < N; j++) {
+                const double dx = px[i] - px[j], dy = py[i] - py[j];
+                viol_c |= (dx * dx + dy * dy) <= p.collision_thr2;
+            }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            px[i] = px[i] + kTimeStep * cs[i] * v[i];
+            py[i] = py[i] + kTimeStep * sn[i] * v[i];
+            double t = th[i] + kTimeStep * om[i];
+            // atan2(sin t, cos t) for |t| < pi + 0.12: wrap into (-pi, pi]
+            t = t > kPi ? t - kTwoPi : (t < -kPi ? t + kTwoPi : t);
+            th[i] = t;
+            const double c2 = cs[i] * cd[i] - sn[i] * sd[i];               // heading advanced by dt*omega
+            sn[i] = sn[i] * cd[i] + cs[i] * sd[i];
+            cs[i] = c2;
+        }
+        if (c.penalize_violations && (viol_c || viol_b)) {                  // roboEnv.py:82-94
+            msg = (viol_c ? 1 : 0) + (viol_b ? 2 : 0);
+#pragma unroll
+            for (int i = 0; i < N; i++) dist[i] += kTimeStep * fabs(v[i]);
+            break;
+        }
+    }
+
+    // ---------------------------------------------------------------- scenario tail (order matters)
+    const int D = p.obs_dim;
+    float *obs = p.buf.obs + env * (int64_t)(N * D);
+    float rew[N];
+    bool done = false;
+    int remaining = 0, scen_metric = 0;
+
+    if (SCN == MRB_PCP) {
+        const int P = c.num_prey;
+        uint32_t sensed = (uint32_t)sci[0], captured = (uint32_t)sci[S];
+        const int unseen0 = P - __popc(sensed), left0 = P - __popc(captured);
+        double bd[N], bx[N], by[N];
+#pragma unroll
+        for (int a = 0; a < N; a++) { bd[a] = -1.0; bx[a] = -5.0; by[a] = -5.0; }
+        for (int q = 0; q < P; q++) {
+            if ((captured >> q) & 1) continue;
+            const double qxp = scf[(2 * q) * S], qyp = scf[(2 * q + 1) * S];
+            double d2[N];
+            bool sense = false, capture = false;
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                const double dx = px[a] - qxp, dy = py[a] - qyp;
+                d2[a] = dx * dx + dy * dy;
+                // _update_tracking_and_locations (PredatorCapturePrey.py:72-95): predators sense
+                // (capture agents have sensing radius 0), capture agents capture on 'no_action'
+                const bool pred = a < c.num_predators;
+                sense |= d2[a] <= (pred ? p.sense_thr2 : 0.0);
+                capture |= (act[a] == 4) && d2[a] <= (pred ? 0.0 : p.capture_thr2);
+            }
+            if (sense) sensed |= 1u << q;
+            if (((sensed >> q) & 1) && capture) { captured |= 1u << q; continue; }
+            // Agent.get_observation (agent.py:19-46): closest uncaptured prey inside own sensing radius
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                const bool in_range = d2[a] <= (a < c.num_predators ? p.sense_thr2 : 0.0);
+                if (in_range && (bd[a] < 0.0 || d2[a] < bd[a])) { bd[a] = d2[a]; bx[a] = qxp; by[a] = qyp; }
+            }
+        }
+        const int unseen = P - __popc(sensed), left = P - __popc(captured);
+        sci[0] = (int32_t)sensed; sci[S] = (int32_t)captured;
+        // get_observations (PredatorCapturePrey.py:178-207)
+        const int od = c.capability_aware ? 6 : 4;
+#pragma unroll
+        for (int a = 0; a < N; a++) {
+            int slot = 0;
+            auto put = [&](int b) {
+                float *o = obs + a * D + slot * od;
+                o[0] = (float)px[b]; o[1] = (float)py[b]; o[2] = (float)bx[b]; o[3] = (float)by[b];
+                if (od == 6) {
+                    o[4] = (float)(b < c.num_predators ? c.predator_radius : 0.0);
+                    o[5] = (float)(b < c.num_predators ? 0.0 : c.capture_radius);
+                }
+                slot++;
+            };
+            put(a);
+            if (c.num_neighbors >= N - 1) {
+#pragma unroll
+                for (int b = 0; b < N; b++) if (b != a) put(b);
+            } else {                                   // utilities/misc.py:20-25: K nearest, ascending distance
+                uint32_t used = 1u << a;
+                for (int kk = 0; kk < c.num_neighbors; kk++) {
+                    int best = -1; double bdist = 0.0;
+#pragma unroll
+                    for (int b = 0; b < N; b++) {
+                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = dx * dx + dy * dy;
+                        if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
+                    }
+                    used |= 1u << best;
+#pragma unroll
+                    for (int b = 0; b < N; b++) if (b == best) put(b);
+                }
+            }
+        }
+        float r;
+        if (msg) { r = (float)c.violation_reward; done = true; }           // PredatorCapturePrey.py:155-159
+        else {                                                             // get_rewards (:209-216)
+            r = (float)(((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty);
+            done = steps > c.max_episode_steps || left == 0;
+        }
+#pragma unroll
+        for (int a = 0; a < N; a++) rew[a] = r;
+        remaining = left; scen_metric = P - left;
+    } else if (SCN == MRB_WAREHOUSE) {
+        uint32_t loaded = (uint32_t)sci[0];
+#pragma unroll
+        for (int a = 0; a < N; a++) {                                       // get_observations (warehouse.py:124-143)
+            int slot = 0;
+            auto put = [&](int b) {
+                float *o = obs + a * D + slot * 3;
+                o[0] = (float)px[b]; o[1] = (float)py[b]; o[2] = (float)((loaded >> b) & 1);
+                slot++;
+            };
+            put(a);
+            if (c.num_neighbors >= N - 1) {
+#pragma unroll
+                for (int b = 0; b < N; b++) if (b != a) put(b);
+            } else {
+                uint32_t used = 1u << a;
+                for (int kk = 0; kk < c.num_neighbors; kk++) {
+                    int best = -1; double bdist = 0.0;
+#pragma unroll
+                    for (int b = 0; b < N; b++) {
+                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = dx * dx + dy * dy;
+                        if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
+                    }
+                    used |= 1u << best;
+#pragma unroll
+                    for (int b = 0; b < N; b++) if (b == best) put(b);
+                }
+            }
+        }
+        if (msg) {
+#pragma unroll
+            for (int a = 0; a < N; a++) rew[a] = (float)c.violation_reward;
+            done = true;
+        } else {                                                            // get_rewards (:145-178)
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                const bool green = (a % 2 == 0), ld = (loaded >> a) & 1;    // even index -> Green (:63-65)
+                double r = 0.0;
+                if (ld) {
+                    if (px[a] < -1.5 + c.goal_width && ((green && py[a] > 0) || (!green && py[a] <= 0))) {
+                        r = c.unload_reward; loaded &= ~(1u << a); scen_metric++;
+                    }
+                } else {
+                    if (px[a] > 1.5 - c.goal_width && ((!green && py[a] > 0) || (green && py[a] <= 0))) {
+                        r = c.load_reward; loaded |= 1u << a;
+                    }
+                }
+                rew[a] = (float)r;
+            }
+            done = steps > c.max_episode_steps;
+        }
+        sci[0] = (int32_t)loaded;
+    } else if (SCN == MRB_MATERIAL) {
+        int load[N], zone[2];
+#pragma unroll
+        for (int a = 0; a < N; a++) load[a] = sci[a * S];
+        zone[0] = sci[N * S]; zone[1] = sci[(N + 1) * S];
+        int messages = 0;
+#pragma unroll
+        for (int i = 0; i < 4 && i < N; i++) messages |= (act[i] % 4) << (2 * i);   // MaterialTransport.py:119-120
+#pragma unroll
+        for (int a = 0; a < N; a++) {                                       // get_observations (:150-159)
+            float *o = obs + a * D;
+            o[0] = (float)px[a]; o[1] = (float)py[a]; o[2] = (float)load[a];
+            o[3] = (float)zone[0]; o[4] = (float)zone[1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[5 + i] = (float)((messages >> (2 * i)) & 3);
+            if (c.capability_aware) {
+                o[9] = (float)(a < c.n_fast ? c.small_torque : c.large_torque);
+                o[10] = (float)(a < c.n_fast ? c.fast_step : c.slow_step);
+            }
+        }
+        double r;
+        if (msg) { r = c.violation_reward; done = true; }
+        else {                                                              // get_reward (:161-189)
+            r = c.time_penalty;
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                const int torque = a < c.n_fast ? c.small_torque : c.large_torque;
+                if (load[a] > 0) {
+                    if (px[a] < -1.5 + c.goal_width) { r += load[a] * c.unload_reward; scen_metric += load[a]; load[a] = 0; }
+                } else {
+                    int zi = -1;
+                    if (px[a] > 1.5 - c.goal_width) zi = 1;
+                    else if (px[a] * px[a] + py[a] * py[a] <= p.zone1_thr2) zi = 0;
+                    if (zi >= 0) {
+                        const int zl = zi ? zone[1] : zone[0];
+                        const int take = zl > torque ? torque : zl;
+                        load[a] = take;
+                        if (zi) zone[1] = zl - take; else zone[0] = zl - take;
+                        r += take * c.load_reward;
+                    }
+                }
+            }
+            done = steps > c.max_episode_steps;
+            if (!done) {
+                bool empty = zone[0] == 0 && zone[1] == 0;
+#pragma unroll
+                for (int a = 0; a < N; a++) empty &= load[a] == 0;
+                done = empty;
+            }
+        }
+        remaining = zone[0] + zone[1];
+#pragma unroll
+        for (int a = 0; a < N; a++) { rew[a] = (float)r; remaining += load[a]; sci[a * S] = load[a]; }
+        sci[N * S] = zone[0]; sci[(N + 1) * S] = zone[1]; sci[(N + 2) * S] = messages;
+    } else if (SCN == MRB_ARCTIC) {
+        uint32_t g[6];
+#pragma unroll
+        for (int t = 0; t < 6; t++) g[t] = (uint32_t)sci[t * S];
+        const int goal_col = sci[6 * S];
+        int row[N], col[N], pix[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            arctic_cell(px[i], py[i], row[i], col[i]);
+            pix[i] = arctic_grid(g, row[i], col[i]);
+        }
+        const double goalx = goal_col * .25 - 1.5, goaly = (-1 * .25 + .75);  // get_pose_from_cell([1, g])
+        float nb[16];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {                                       // agent.py:73-85
+            const int left = col[i] > 0 ? col[i] - 1 : col[i], right = col[i] < 11 ? col[i] + 1 : col[i];
+            const int up = row[i] > 0 ? row[i] - 1 : row[i], down = row[i] < 7 ? row[i] + 1 : row[i];
+            nb[8 * i + 0] = (float)arctic_grid(g, up, left);   nb[8 * i + 1] = (float)arctic_grid(g, row[i], left);
+            nb[8 * i + 2] = (float)arctic_grid(g, down, left); nb[8 * i + 3] = (float)arctic_grid(g, up, col[i]);
+            nb[8 * i + 4] = (float)arctic_grid(g, down, col[i]); nb[8 * i + 5] = (float)arctic_grid(g, up, right);
+            nb[8 * i + 6] = (float)arctic_grid(g, row[i], right); nb[8 * i + 7] = (float)arctic_grid(g, down, right);
+        }
+        at_pix = 0;
+#pragma unroll
+        for (int a = 0; a < N; a++) {                                       // Agent.get_observation (agent.py:14-87)
+            at_pix |= pix[a] << (2 * a);
+            if (pix[a] == 3) at_reached |= 1 << a;
+            constexpr int perm[4][3] = {{1, 2, 3}, {0, 2, 3}, {3, 0, 1}, {2, 0, 1}};   // agent.py:42-69
+            float *o = obs + a * D;
+            o[0] = (float)px[a]; o[1] = (float)py[a]; o[2] = (float)pix[a];
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const int b = perm[a & 3][t];
+                o[3 + 3 * t] = (float)px[b]; o[4 + 3 * t] = (float)py[b]; o[5 + 3 * t] = (float)pix[b];
+            }
+            o[12] = (float)goalx; o[13] = (float)goaly;
+#pragma unroll
+            for (int t = 0; t < 16; t++) o[14 + t] = nb[t];
+        }
+        double r;
+        if (msg) { r = c.violation_reward; done = true; }
+        else {                                                              // get_reward (ArcticTransport.py:125-134)
+            r = 0.0;
+            bool all_reached = true;
+#pragma unroll
+            for (int a = 2; a < N; a++) {
+                const bool reached = (at_reached >> a) & 1;
+                if (!reached) r += c.not_reached_penalty;
+                if (pix[a] != 3) {
+                    const double dx = px[a] - goalx, dy = py[a] - goaly;
+                    r += c.dist_multiplier * (dx * dx + dy * dy);
+                }
+                all_reached &= reached;
+            }
+            done = steps > c.max_episode_steps || all_reached;
+            scen_metric = all_reached ? 1 : 0;
+        }
+#pragma unroll
+        for (int a = 0; a < N; a++) rew[a] = (float)r;
+        sci[7 * S] = at_pix; sci[8 * S] = at_reached;
+    } else {                                                                // Simple (simple.py:155-225)
+        const double goalx = scf[0], goaly = scf[S];
+#pragma unroll
+        for (int a = 0; a < N; a++) {
+            float *o = obs + a * D;
+            int k = 0;
+            o[k++] = (float)px[a]; o[k++] = (float)py[a];
+#pragma unroll
+            for (int b = 0; b < N; b++) if (b != a) { o[k++] = (float)px[b]; o[k++] = (float)py[b]; }
+            o[k++] = (float)goalx; o[k++] = (float)goaly;
+            const double dx = px[a] - goalx, dy = py[a] - goaly;
+            rew[a] = msg ? (float)c.violation_reward : (float)(-(dx * dx + dy * dy) * c.reward_scaler);
+        }
+        done = msg != 0 || steps > c.max_episode_steps;
+    }
+
+    // ---------------------------------------------------------------- write back
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        sf[i * S] = px[i]; sf[(N + i) * S] = py[i]; sf[(2 * N + i) * S] = th[i];
+        sf[(3 * N + i) * S] = qx[i]; sf[(4 * N + i) * S] = qy[i];
+    }
+    si[0] = steps;
+    si[S] = 1;
+    float team = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        p.buf.reward[env * N + i] = rew[i];
+        team += rew[i];
+        if (p.buf.dist) p.buf.dist[env * N + i] = (float)dist[i];
+    }
+    p.buf.done[env] = done ? 1 : 0;
+    p.buf.message[env] = (uint8_t)msg;
+    p.buf.remaining[env] = remaining;
+    const double ep_return = sf[(5 * N) * S] + (double)team;
+    sf[(5 * N) * S] = ep_return;
+
+    if (c.collect_stats && p.buf.stats) {
+        double *st = p.buf.stats;
+        const unsigned active = __activemask();
+        const int w_it = __reduce_add_sync(active, n_it), w_qp = __reduce_add_sync(active, n_qp);
+        const int w_n = __popc(active);
+        if ((threadIdx.x & 31) == __ffs(active) - 1) {
+            atomicAdd(st + MRB_STAT_ENV_STEPS, (double)w_n);
+            atomicAdd(st + MRB_STAT_QP_SOLVES, (double)w_qp);
+            atomicAdd(st + MRB_STAT_QP_ITERS, (double)w_it);
+        }
+        if (done) {
+            atomicAdd(st + MRB_STAT_EPISODES, 1.0);
+            atomicAdd(st + MRB_STAT_RETURN, ep_return);
+            atomicAdd(st + MRB_STAT_LENGTH, (double)steps);
+            if (msg & 1) atomicAdd(st + MRB_STAT_COLLISION, 1.0);
+            if (msg & 2) atomicAdd(st + MRB_STAT_BOUNDARY, 1.0);
+            if (!msg && steps > c.max_episode_steps) atomicAdd(st + MRB_STAT_TIMEOUTS, 1.0);
+            atomicAdd(st + MRB_STAT_SCENARIO, (double)scen_metric);
+        }
+    }
+    if (done && c.auto_reset) reset_env<SCN>(p, env);
+}
+
+}  // namespace mrb

