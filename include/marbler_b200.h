@@ -76,7 +76,8 @@ typedef struct mrb_config {
 #define MRB_NUM_STATS 16
 enum { MRB_STAT_EPISODES = 0, MRB_STAT_RETURN = 1, MRB_STAT_LENGTH = 2, MRB_STAT_COLLISION = 3,
        MRB_STAT_BOUNDARY = 4, MRB_STAT_SCENARIO = 5, MRB_STAT_ENV_STEPS = 6, MRB_STAT_QP_SOLVES = 7,
-       MRB_STAT_QP_ITERS = 8, MRB_STAT_TIMEOUTS = 9 };
+       MRB_STAT_QP_ITERS = 8, MRB_STAT_TIMEOUTS = 9,
+       MRB_STAT_QP_STALLS = 10 /* solves that ran >= 25 iterations: cvxopt's iteration caught in a limit cycle */ };
 typedef struct mrb_buffers {
     double *state_f64;
     int32_t *state_i32;

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libmarbler_b200.so")
 ABI_VERSION = 1
 NUM_STATS = 16
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "collisions", "boundary_exits", "scenario_metric",
-              "env_steps", "qp_solves", "qp_iterations", "timeouts")
+              "env_steps", "qp_solves", "qp_iterations", "timeouts", "qp_stalls")
 SYMBOLS = ("mrb_version", "mrb_create", "mrb_destroy", "mrb_last_error", "mrb_state_rows", "mrb_obs_dim",
            "mrb_num_actions", "mrb_bind", "mrb_reset", "mrb_step", "mrb_step_host", "mrb_barrier_qp",
            "mrb_launch_count")

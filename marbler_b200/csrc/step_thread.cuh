@@ -71,8 +71,9 @@ __device__ __forceinline__ void spawn_grid(const mrb_spawn &sp, Philox &g, F emi
         }
         taken |= 1ull << cell;
         const int ix = cell / sp.yr, iy = cell % sp.yr;
-        const double x = ((ix * sp.spacing - sp.w2) + sp.sx1) + sp.sx2;
-        const double y = ((iy * sp.spacing - sp.h2) + sp.sy1) + sp.sy2;
+        // explicit _rn ops: no FMA contraction, so the spawn poses are bit-identical to numpy's
+        const double x = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn((double)ix, sp.spacing), sp.w2), sp.sx1), sp.sx2);
+        const double y = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn((double)iy, sp.spacing), sp.h2), sp.sy1), sp.sy2);
         double th = 0.0;
         if (sp.random_theta) {                       // warehouse.py:93 keeps rps' random heading
             th = g.unit() * kTwoPi - kPi;
@@ -202,7 +203,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             dist[i] = sqrt(dx * dx + dy * dy);
         }
     }
-    int msg = 0, n_qp = 0, n_it = 0;
+    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0;
     const int UF = c.update_frequency;
     for (int k = 0; k < UF; k++) {                // roboEnv.py:52
         // :55-56 for k >= 1: |pose_k - pose_{k-1}| = dt |v_{k-1}| (c^2 + s^2 = 1)
@@ -228,7 +229,9 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                 ux[i] = dx; uy[i] = dy;
             }
             QpThread<N> qp;
-            n_it += qp.run(xix, xiy, ux, uy, c.barrier_default != 0);      // controller.py:23
+            const int it = qp.run(xix, xiy, ux, uy, c.barrier_default != 0);   // controller.py:23
+            n_it += it;
+            n_stall += it >= 25;
             n_qp++;
 #pragma unroll
             for (int i = 0; i < N; i++) {                                   // si_to_uni_dyn (A.7) + saturation (A.2)
@@ -561,11 +564,12 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         double *st = p.buf.stats;
         const unsigned active = __activemask();
         const int w_it = __reduce_add_sync(active, n_it), w_qp = __reduce_add_sync(active, n_qp);
-        const int w_n = __popc(active);
+        const int w_n = __popc(active), w_stall = __reduce_add_sync(active, n_stall);
         if ((threadIdx.x & 31) == __ffs(active) - 1) {
             atomicAdd(st + MRB_STAT_ENV_STEPS, (double)w_n);
             atomicAdd(st + MRB_STAT_QP_SOLVES, (double)w_qp);
             atomicAdd(st + MRB_STAT_QP_ITERS, (double)w_it);
+            if (w_stall) atomicAdd(st + MRB_STAT_QP_STALLS, (double)w_stall);
         }
         if (done) {
             atomicAdd(st + MRB_STAT_EPISODES, 1.0);

@@ -231,13 +231,13 @@ class COracle(object):
 
     # ---------------------------------------------------------------- flat drivers
     def step_flat(self, sf, si, actions, auto_reset=False, seed=0, env_id0=0, threads=1):
-        """In place on (sf, si).  Returns obs[B,N,D], reward[B,N], dist[B,N], out_i[B,5]."""
+        """In place on (sf, si).  Returns obs[B,N,D], reward[B,N], dist[B,N], out_i[B,6]."""
         B = sf.shape[0]
         actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(B, self.N)
         obs = np.empty((B, self.N, self.D))
         rew = np.empty((B, self.N))
         dist = np.empty((B, self.N))
-        out_i = np.empty((B, 5), dtype=np.int32)
+        out_i = np.empty((B, 6), dtype=np.int32)
         L = lib()
         dp, ip = C.c_double, C.c_int32
 
@@ -269,7 +269,7 @@ class COracle(object):
         obs, rew, dist, out_i = self.step_flat(sf, si, actions)
         out = {"obs": obs, "reward": rew, "dist": dist, "message": out_i[:, 0].copy(),
                "done": out_i[:, 1].astype(np.bool_), "remaining": out_i[:, 2].copy(),
-               "qp_evals": out_i[:, 3].copy(), "qp_iters": out_i[:, 4].copy()}
+               "qp_evals": out_i[:, 3].copy(), "qp_iters": out_i[:, 4].copy(), "qp_max_iters": out_i[:, 5].copy()}
         if not batched:
             out = {k: v[0] for k, v in out.items()}
             out["done"] = np.full(self.N, out["done"], dtype=np.bool_)

@@ -402,7 +402,7 @@ void orc_step(const orc_config *c, double *sf, int32_t *si, const int32_t *actio
     double *pose = sf, *prev = sf + 3 * N, *scf = sf + 6 * N;
     int32_t *sci = si + 3;
     double goal[2 * NMAX], vel[2 * NMAX];
-    int msg = 0, n_qp = 0, n_it = 0;
+    int msg = 0, n_qp = 0, n_it = 0, max_it = 0;
 
     si[0] += 1;                                          /* episode_steps, first line of every step() */
 
@@ -424,7 +424,9 @@ void orc_step(const orc_config *c, double *sf, int32_t *si, const int32_t *actio
         memcpy(prev, pose, sizeof(double) * 3 * N);      /* :59 */
         si[1] = 1;
         if (k % c->ctrl_period == 0 || c->robotarium) {  /* :63-65 */
-            n_it += orc_controller(N, c->barrier_default, pose, goal, vel);
+            int it = orc_controller(N, c->barrier_default, pose, goal, vel);
+            n_it += it;
+            if (it > max_it) max_it = it;
             n_qp++;
         }
         /* Robotarium.step (A.3): validate on the entering pose (A.4), then integrate in place */
@@ -641,7 +643,7 @@ void orc_step(const orc_config *c, double *sf, int32_t *si, const int32_t *actio
             done = si[0] > c->max_episode_steps;
         }
     }
-    out_i[0] = msg; out_i[1] = done; out_i[2] = remaining; out_i[3] = n_qp; out_i[4] = n_it;
+    out_i[0] = msg; out_i[1] = done; out_i[2] = remaining; out_i[3] = n_qp; out_i[4] = n_it; out_i[5] = max_it;
 }
 
 /* ------------------------------------------------------------------ reset (distributional parity)
@@ -752,7 +754,7 @@ void orc_step_batch(const orc_config *c, int64_t B, double *sf, int32_t *si, con
     const int nf = orc_nf(c), ni = orc_ni(c), N = c->N, D = orc_obs_dim(c);
     for (int64_t b = 0; b < B; b++) {
         orc_step(c, sf + b * nf, si + b * ni, actions + b * N, obs + b * N * D, reward + b * N,
-                 dist + b * N, out_i + b * 5);
-        if (auto_reset && out_i[b * 5 + 1]) orc_reset(c, seed, env_id0 + (uint64_t)b, sf + b * nf, si + b * ni);
+                 dist + b * N, out_i + b * 6);
+        if (auto_reset && out_i[b * 6 + 1]) orc_reset(c, seed, env_id0 + (uint64_t)b, sf + b * nf, si + b * ni);
     }
 }
