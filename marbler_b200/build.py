@@ -26,19 +26,35 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or older than its sources.  Returns the .so path."""
+    """Compile the CUDA library if it is missing or older than its sources (one nvcc per translation
+    unit, in parallel, then one link).  Returns the .so path."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("marbler_b200: nvcc not found and %s is missing/stale" % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "capi.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("marbler_b200: nvcc failed\n" + res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(u):
+        obj = os.path.join(objdir, u[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, u)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("marbler_b200: nvcc failed on %s\n%s%s" % (u, res.stdout, res.stderr))
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max(1, min(len(units), os.cpu_count() or 1))) as ex:
+        results = list(ex.map(compile_one, units))
     if verbose:
-        print(res.stderr)
+        for _, log in results:
+            print(log)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [o for o, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("marbler_b200: link failed\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -7,8 +7,8 @@
 #include <new>
 #include <string>
 
-#include "step_thread.cuh"
-#include "step_warp.cuh"
+#include "common.cuh"
+#include "launchers.h"
 
 using namespace mrb;
 
@@ -159,14 +159,6 @@ extern "C" int mrb_bind(mrb_env *env, const mrb_buffers *b)
     return MRB_OK;
 }
 
-template <int SCN>
-static void launch_reset(mrb_env *e, const uint8_t *mask, cudaStream_t s)
-{
-    const int tpb = 128;
-    reset_kernel<SCN><<<(unsigned)((e->p.B + tpb - 1) / tpb), tpb, 0, s>>>(e->p, mask);
-    g_launches++;
-}
-
 extern "C" int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void *stream)
 {
     if (!env) return MRB_E_ARG;
@@ -175,40 +167,9 @@ extern "C" int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void 
     if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
     env->p.seed = seed;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (env->p.cfg.scenario) {
-    case MRB_PCP: launch_reset<MRB_PCP>(env, mask, s); break;
-    case MRB_WAREHOUSE: launch_reset<MRB_WAREHOUSE>(env, mask, s); break;
-    case MRB_MATERIAL: launch_reset<MRB_MATERIAL>(env, mask, s); break;
-    case MRB_ARCTIC: launch_reset<MRB_ARCTIC>(env, mask, s); break;
-    default: launch_reset<MRB_SIMPLE>(env, mask, s); break;
-    }
+    if ((st = launch_reset(env->p, mask, s)) != cudaSuccess) return cuda_fail(env, st, "reset kernel launch");
+    g_launches++;
     if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(env, st, "reset kernel launch");
-    return MRB_OK;
-}
-
-template <int SCN, int N>
-static void launch_thread(mrb_env *e, const int32_t *actions, cudaStream_t s)
-{
-    const unsigned grid = (unsigned)((e->p.B + kThreadsPerBlock - 1) / kThreadsPerBlock);
-    step_thread_kernel<SCN, N><<<grid, kThreadsPerBlock, 0, s>>>(e->p, actions);
-    g_launches++;
-}
-template <int SCN>
-static void launch_warp(mrb_env *e, const int32_t *actions, cudaStream_t s)
-{
-    launch_step_warp<SCN>(e->p, actions, s);
-    g_launches++;
-}
-
-template <int SCN>
-static int dispatch_step(mrb_env *e, const int32_t *actions, cudaStream_t s)
-{
-    switch (e->p.cfg.num_robots) {
-    case 4: launch_thread<SCN, 4>(e, actions, s); return MRB_OK;
-    default: break;
-    }
-    if (SCN == MRB_ARCTIC) return MRB_E_UNSUPPORTED;
-    launch_warp<SCN>(e, actions, s);
     return MRB_OK;
 }
 
@@ -220,15 +181,18 @@ extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
     cudaError_t st = cudaSetDevice(env->device);
     if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
     cudaStream_t s = (cudaStream_t)stream;
-    int rc;
+    // teams of up to kMaxThreadRobots robots: one env per thread (registers); larger teams: one env per warp
+    bool launched = false;
     switch (env->p.cfg.scenario) {
-    case MRB_PCP: rc = dispatch_step<MRB_PCP>(env, actions, s); break;
-    case MRB_WAREHOUSE: rc = dispatch_step<MRB_WAREHOUSE>(env, actions, s); break;
-    case MRB_MATERIAL: rc = dispatch_step<MRB_MATERIAL>(env, actions, s); break;
-    case MRB_ARCTIC: rc = dispatch_step<MRB_ARCTIC>(env, actions, s); break;
-    default: rc = dispatch_step<MRB_SIMPLE>(env, actions, s); break;
+    case MRB_PCP: st = launch_step_pcp(env->p, actions, s, &launched); break;
+    case MRB_WAREHOUSE: st = launch_step_warehouse(env->p, actions, s, &launched); break;
+    case MRB_MATERIAL: st = launch_step_material(env->p, actions, s, &launched); break;
+    case MRB_ARCTIC: st = launch_step_arctic(env->p, actions, s, &launched); break;
+    default: st = launch_step_simple(env->p, actions, s, &launched); break;
     }
-    if (rc != MRB_OK) return fail(env, rc, "mrb_step: no kernel for this (scenario, num_robots)");
+    if (st != cudaSuccess) return cuda_fail(env, st, "step kernel launch");
+    if (!launched) return fail(env, MRB_E_UNSUPPORTED, "mrb_step: no kernel for this (scenario, num_robots)");
+    g_launches++;
     if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(env, st, "step kernel launch");
     return MRB_OK;
 }
@@ -261,27 +225,6 @@ extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *o
     return MRB_OK;
 }
 
-// ---- barrier QP alone
-template <int N>
-__global__ void __launch_bounds__(kThreadsPerBlock)
-qp_thread_kernel(int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
-                 double *__restrict__ u, int32_t *__restrict__ iters)
-{
-    const int64_t e = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
-    if (e >= B) return;
-    double xix[N], xiy[N], ux[N], uy[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        xix[i] = xi[i * B + e]; xiy[i] = xi[(N + i) * B + e];
-        ux[i] = dxi[i * B + e]; uy[i] = dxi[(N + i) * B + e];
-    }
-    QpThread<N> qp;
-    const int it = qp.run(xix, xiy, ux, uy, barrier_default != 0);
-#pragma unroll
-    for (int i = 0; i < N; i++) { u[i * B + e] = ux[i]; u[(N + i) * B + e] = uy[i]; }
-    if (iters) iters[e] = it;
-}
-
 extern "C" int mrb_barrier_qp(int device, int32_t N, int32_t barrier_default, int64_t B, const double *dxi,
                               const double *xi, double *u, int32_t *iters, void *stream)
 {
@@ -289,13 +232,7 @@ extern "C" int mrb_barrier_qp(int device, int32_t N, int32_t barrier_default, in
     cudaError_t st = cudaSetDevice(device);
     if (st != cudaSuccess) return cuda_fail(nullptr, st, "cudaSetDevice");
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock);
-    switch (N) {
-    case 2: qp_thread_kernel<2><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 3: qp_thread_kernel<3><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 4: qp_thread_kernel<4><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    default: launch_qp_warp(N, barrier_default, B, dxi, xi, u, iters, s); break;
-    }
+    if ((st = launch_barrier_qp(N, barrier_default, B, dxi, xi, u, iters, s)) != cudaSuccess) return cuda_fail(nullptr, st, "qp kernel launch");
     g_launches++;
     if ((st = cudaGetLastError()) != cudaSuccess) return cuda_fail(nullptr, st, "qp kernel launch");
     return MRB_OK;

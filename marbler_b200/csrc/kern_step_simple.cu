@@ -1,0 +1,7 @@
+#include "step_dispatch.cuh"
+namespace mrb {
+cudaError_t launch_step_simple(const Params &p, const int32_t *actions, cudaStream_t s, bool *launched)
+{
+    return launch_step_generic<MRB_SIMPLE>(p, actions, s, launched);
+}
+}  // namespace mrb

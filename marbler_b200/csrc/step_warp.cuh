@@ -1,8 +1,682 @@
-// placeholder until the warp-per-env kernels land
+// One environment per WARP: the general path for teams that do not fit the one-env-per-thread
+// kernel (more than 6 robots, up to 32).  Lane i owns robot i (pose, goal, velocity); the pair
+// constraints of the barrier QP are distributed round-robin over the lanes (slot k of lane l is
+// pair l + 32 k); the 2N x 2N KKT matrix and the small vectors live in a per-warp shared-memory
+// workspace.  Same algorithm, constants and reference citations as step_thread.cuh / qp_thread.cuh.
 #pragma once
 #include "common.cuh"
+
 namespace mrb {
-template <int SCN>
-inline void launch_step_warp(const Params &, const int32_t *, cudaStream_t) {}
-inline void launch_qp_warp(int, int, int64_t, const double *, const double *, double *, int32_t *, cudaStream_t) {}
+
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
 }
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }   // a < b
+
+__host__ __device__ inline int qp_ld(int n) { return n | 1; }
+__host__ __device__ inline size_t warp_workspace_doubles(int N)
+{
+    const int n = 2 * N, m = N * (N - 1) / 2;
+    return (size_t)n * qp_ld(n) + 6 * (size_t)n + 5 * (size_t)(m > 0 ? m : 1);
+}
+
+template <int PPL>
+struct QpWarp {
+    int N, n, m, ld, lane;
+    double *K, *invd, *vx, *vq, *vrx, *vdx, *xix, *xiy, *pax, *pay, *pw, *pz, *pt;
+    int pi[PPL], pj[PPL];
+    bool pv[PPL];
+    double ax[PPL], ay[PPL], h[PPL];
+
+    __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), ld(qp_ld(2 * N_)), lane(lane_)
+    {
+        K = ws; invd = K + (size_t)n * ld; vx = invd + n; vq = vx + n; vrx = vq + n; vdx = vrx + n;
+        xix = vdx + n; xiy = xix + N; pax = xiy + N; pay = pax + m; pw = pay + m; pz = pw + m; pt = pz + m;
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {                   // decode my pair slots once
+            const int c = lane + 32 * k;
+            pv[k] = c < m;
+            int i = 0, rem = pv[k] ? c : 0;
+            while (rem >= N - 1 - i) { rem -= N - 1 - i; i++; }
+            pi[k] = i; pj[k] = i + 1 + rem;
+        }
+    }
+
+    __device__ __forceinline__ void G_mul(const double *v, double (&out)[PPL]) const
+    {
+#pragma unroll
+        for (int k = 0; k < PPL; k++)
+            out[k] = pv[k] ? ax[k] * (v[2 * pj[k]] - v[2 * pi[k]]) + ay[k] * (v[2 * pj[k] + 1] - v[2 * pi[k] + 1]) : 0.0;
+    }
+    // out (smem, robot lanes) += G' y, y in smem indexed by pair
+    __device__ __forceinline__ void GT_acc(const double *y, double *out) const
+    {
+        if (lane < N) {
+            double sx = 0.0, sy = 0.0;
+            for (int j = 0; j < N; j++) {
+                if (j == lane) continue;
+                const int c = lane < j ? pair_index(lane, j, N) : pair_index(j, lane, N);
+                const double t = lane < j ? -y[c] : y[c];
+                sx += pax[c] * t; sy += pay[c] * t;
+            }
+            out[2 * lane] += sx; out[2 * lane + 1] += sy;
+        }
+    }
+    // K := 2I + G' diag(pw) G (lower triangle), then in-place Cholesky; invd = 1/diag(L)
+    __device__ void factor()
+    {
+        __syncwarp();
+        if (lane < N) {
+            double dxx = 2.0, dxy = 0.0, dyy = 2.0;
+            for (int j = 0; j < N; j++) {
+                if (j == lane) continue;
+                const int c = lane < j ? pair_index(lane, j, N) : pair_index(j, lane, N);
+                const double wx = pw[c] * pax[c], wy = pw[c] * pay[c];
+                dxx += wx * pax[c]; dxy += wx * pay[c]; dyy += wy * pay[c];
+            }
+            K[(2 * lane) * ld + 2 * lane] = dxx;
+            K[(2 * lane + 1) * ld + 2 * lane] = dxy;
+            K[(2 * lane + 1) * ld + 2 * lane + 1] = dyy;
+        }
+#pragma unroll
+        for (int k = 0; k < PPL; k++)
+            if (pv[k]) {
+                const int c = lane + 32 * k, i = pi[k], j = pj[k];
+                const double wx = pw[c] * ax[k], wy = pw[c] * ay[k];
+                K[(2 * j) * ld + 2 * i] = -wx * ax[k]; K[(2 * j) * ld + 2 * i + 1] = -wx * ay[k];
+                K[(2 * j + 1) * ld + 2 * i] = -wx * ay[k]; K[(2 * j + 1) * ld + 2 * i + 1] = -wy * ay[k];
+            }
+        __syncwarp();
+        for (int j = 0; j < n; j++) {                     // left-looking, one column per step
+            const int r0 = j + lane, r1 = j + lane + 32;
+            double a0 = 0.0, a1 = 0.0;
+            const double *Lj = K + (size_t)j * ld;
+            if (r0 < n) {
+                const double *Lr = K + (size_t)r0 * ld;
+                double acc = Lr[j], acc2 = 0.0;
+                int k = 0;
+                for (; k + 1 < j; k += 2) { acc -= Lr[k] * Lj[k]; acc2 -= Lr[k + 1] * Lj[k + 1]; }
+                if (k < j) acc -= Lr[k] * Lj[k];
+                a0 = acc + acc2;
+            }
+            if (r1 < n) {
+                const double *Lr = K + (size_t)r1 * ld;
+                double acc = Lr[j], acc2 = 0.0;
+                int k = 0;
+                for (; k + 1 < j; k += 2) { acc -= Lr[k] * Lj[k]; acc2 -= Lr[k + 1] * Lj[k + 1]; }
+                if (k < j) acc -= Lr[k] * Lj[k];
+                a1 = acc + acc2;
+            }
+            const double d = __shfl_sync(kFull, a0, 0);
+            double r = rsqrt(d);
+            r = r * (1.5 - 0.5 * d * r * r);
+            __syncwarp();
+            if (r0 < n) K[(size_t)r0 * ld + j] = a0 * r;
+            if (r1 < n) K[(size_t)r1 * ld + j] = a1 * r;
+            if (lane == 0) invd[j] = r;
+            __syncwarp();
+        }
+    }
+    // b (smem) := K^-1 b
+    __device__ void solve(double *b) const
+    {
+        __syncwarp();
+        double b0 = lane < n ? b[lane] : 0.0, b1 = lane + 32 < n ? b[lane + 32] : 0.0;
+        for (int k = 0; k < n; k++) {
+            const double bk = __shfl_sync(kFull, (k >> 5) ? b1 : b0, k & 31);
+            const double xk = bk * invd[k];
+            if (lane == (k & 31)) { if (k >> 5) b1 = xk; else b0 = xk; }
+            if (lane > k && lane < n) b0 -= K[(size_t)lane * ld + k] * xk;
+            if (lane + 32 > k && lane + 32 < n) b1 -= K[(size_t)(lane + 32) * ld + k] * xk;
+        }
+        for (int k = n - 1; k >= 0; k--) {
+            const double bk = __shfl_sync(kFull, (k >> 5) ? b1 : b0, k & 31);
+            const double xk = bk * invd[k];
+            if (lane == (k & 31)) { if (k >> 5) b1 = xk; else b0 = xk; }
+            const double *Lk = K + (size_t)k * ld;
+            if (lane < k) b0 -= Lk[lane] * xk;
+            if (lane + 32 < k) b1 -= Lk[lane + 32] * xk;
+        }
+        if (lane < n) b[lane] = b0;
+        if (lane + 32 < n) b[lane + 32] = b1;
+        __syncwarp();
+    }
+
+    // lane i < N holds (xi, nominal dxi -> certified u) of robot i.  Returns IPM iterations.
+    __device__ int run(double xi_x, double xi_y, double &ux, double &uy, bool barrier_default)
+    {
+        if (lane < N) {
+            const double nrm = sqrt(ux * ux + uy * uy);
+            if (nrm > kQpMagnitudeLimit) { const double sc = kQpMagnitudeLimit / nrm; ux *= sc; uy *= sc; }
+        }
+        if (m == 0) return 0;
+        __syncwarp();
+        if (lane < N) {
+            xix[lane] = xi_x; xiy[lane] = xi_y;
+            vq[2 * lane] = -2.0 * ux; vq[2 * lane + 1] = -2.0 * uy;
+        }
+        __syncwarp();
+        const double r2 = barrier_default ? 0.17 * 0.17 : 0.2 * 0.2;
+        double hh = 0.0;
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            ax[k] = ay[k] = h[k] = 0.0;
+            if (pv[k]) {
+                const double ex = xix[pi[k]] - xix[pj[k]], ey = xiy[pi[k]] - xiy[pj[k]];
+                const double hv = (ex * ex + ey * ey) - r2;
+                const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
+                h[k] = gain * (hv * hv * hv);
+                ax[k] = 2.0 * ex; ay[k] = 2.0 * ey;
+                const int c = lane + 32 * k;
+                pax[c] = ax[k]; pay[c] = ay[k]; pw[c] = 1.0; pt[c] = h[k];
+                hh += h[k] * h[k];
+            }
+        }
+        const double qq = warp_sum(lane < N ? 4.0 * (ux * ux + uy * uy) : 0.0);
+        hh = warp_sum(hh);
+        const double resx0 = fmax(1.0, sqrt(qq)), resz0 = fmax(1.0, sqrt(hh));
+
+        // ---- default starting point
+        factor();
+        if (lane < N) { vx[2 * lane] = -vq[2 * lane]; vx[2 * lane + 1] = -vq[2 * lane + 1]; }
+        __syncwarp();
+        GT_acc(pt, vx);
+        solve(vx);
+        double s[PPL], z[PPL];
+        G_mul(vx, z);
+        double ss = 0.0, ts = -INFINITY, tz = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < PPL; k++)
+            if (pv[k]) {
+                z[k] -= h[k];
+                s[k] = -z[k];
+                ss += z[k] * z[k];
+                ts = fmax(ts, z[k]);
+                tz = fmax(tz, -z[k]);
+            } else { s[k] = 1.0; z[k] = 0.0; }
+        ss = warp_sum(ss); ts = warp_max(ts); tz = warp_max(tz);
+        const double nrm = fmax(sqrt(ss), 1.0);
+        double gap = 0.0;
+#pragma unroll
+        for (int k = 0; k < PPL; k++)
+            if (pv[k]) {
+                if (ts >= -1e-8 * nrm) s[k] += 1.0 + ts;
+                if (tz >= -1e-8 * nrm) z[k] += 1.0 + tz;
+                gap += s[k] * z[k];
+            }
+        gap = warp_sum(gap);
+
+        int iters = 0;
+        for (; iters <= 50; iters++) {
+            // rx = 2x + q + G'z ; rz = s + Gx - h
+            double xq = 0.0, xrx = 0.0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) if (pv[k]) pz[lane + 32 * k] = z[k];
+            if (lane < N) {
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const double xv = vx[2 * lane + t], qv = vq[2 * lane + t], r = 2.0 * xv + qv;
+                    vrx[2 * lane + t] = r;
+                    xrx += xv * r; xq += xv * qv;
+                }
+            }
+            __syncwarp();
+            GT_acc(pz, vrx);
+            double rz[PPL];
+            G_mul(vx, rz);
+            double resx = 0.0, resz = 0.0, zrz = 0.0;
+            if (lane < N) resx = vrx[2 * lane] * vrx[2 * lane] + vrx[2 * lane + 1] * vrx[2 * lane + 1];
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    rz[k] += s[k] - h[k];
+                    resz += rz[k] * rz[k];
+                    zrz += z[k] * rz[k];
+                }
+            xq = warp_sum(xq); xrx = warp_sum(xrx); resx = warp_sum(resx); resz = warp_sum(resz); zrz = warp_sum(zrz);
+            const double f0 = 0.5 * (xrx + xq);
+            const double pcost = f0, dcost = f0 + zrz - gap;
+            bool gap_ok = gap <= 1e-7;
+            if (pcost < 0.0) gap_ok = gap_ok || (gap / -pcost <= 1e-2);
+            else if (dcost > 0.0) gap_ok = gap_ok || (gap / dcost <= 1e-2);
+            const double pres = sqrt(resz) / resz0, dres = sqrt(resx) / resx0;
+            if ((pres <= 1e-2 && dres <= 1e-2 && gap_ok) || iters == 50) break;
+
+            double w[PPL], sinv[PPL], t2[PPL], ds[PPL], dz[PPL];
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    sinv[k] = 1.0 / s[k];
+                    w[k] = z[k] * sinv[k];
+                    pw[lane + 32 * k] = w[k];
+                    pt[lane + 32 * k] = z[k] - w[k] * rz[k];
+                } else { sinv[k] = 1.0; w[k] = 0.0; }
+            factor();
+            // predictor
+            if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
+            __syncwarp();
+            GT_acc(pt, vdx);
+            solve(vdx);
+            G_mul(vdx, ds);
+            double dsdz = 0.0, tmax = 0.0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    ds[k] = -rz[k] - ds[k];
+                    dz[k] = -z[k] - w[k] * ds[k];
+                    t2[k] = ds[k] * dz[k];
+                    dsdz += t2[k];
+                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] / z[k]));
+                } else t2[k] = 0.0;
+            dsdz = warp_sum(dsdz); tmax = warp_max(tmax);
+            double step = tmax == 0.0 ? 1.0 : fmin(1.0, 1.0 / tmax);
+            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz / gap * (step * step)));
+            const double sigmamu = sg * sg * sg * (gap / m);
+            // corrector
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    t2[k] = (sigmamu - t2[k]) * sinv[k];
+                    pt[lane + 32 * k] = z[k] - w[k] * rz[k] - t2[k];
+                }
+            if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
+            __syncwarp();
+            GT_acc(pt, vdx);
+            solve(vdx);
+            G_mul(vdx, ds);
+            tmax = 0.0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    ds[k] = -rz[k] - ds[k];
+                    dz[k] = t2[k] - z[k] - w[k] * ds[k];
+                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] / z[k]));
+                }
+            tmax = warp_max(tmax);
+            step = tmax == 0.0 ? 1.0 : fmin(1.0, 0.99 / tmax);
+            if (lane < N) { vx[2 * lane] += step * vdx[2 * lane]; vx[2 * lane + 1] += step * vdx[2 * lane + 1]; }
+            gap = 0.0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++)
+                if (pv[k]) {
+                    s[k] += step * ds[k];
+                    z[k] += step * dz[k];
+                    gap += s[k] * z[k];
+                }
+            gap = warp_sum(gap);
+            __syncwarp();
+        }
+        if (lane < N) { ux = vx[2 * lane]; uy = vx[2 * lane + 1]; }
+        __syncwarp();
+        return iters;
+    }
+};
+
+// ---- the step, lane = robot
+template <int SCN, int PPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    if (env >= p.B) return;
+    const mrb_config &c = p.cfg;
+    const int N = c.num_robots;
+    const int64_t S = p.B;
+    double *sf = p.buf.state_f64 + env;
+    int32_t *si = p.buf.state_i32 + env;
+    int32_t *sci = si + 3 * S;
+    double *scf = sf + (5 * N + 1) * S;
+    QpWarp<PPL> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    const bool me = lane < N;
+
+    double px = 0, py = 0, th = 0, qx = 0, qy = 0;
+    int act = 4;
+    if (me) {
+        px = sf[lane * S]; py = sf[(N + lane) * S]; th = sf[(2 * N + lane) * S];
+        qx = sf[(3 * N + lane) * S]; qy = sf[(4 * N + lane) * S];
+        act = actions[env * N + lane];
+    }
+    const int steps = si[0] + 1;
+    const bool prev_valid = si[S] != 0;
+
+    double gx = px, gy = py;
+    if (me) {
+        const int a = SCN == MRB_MATERIAL ? act / 4 : act;
+        const double stp = SCN == MRB_MATERIAL ? (lane < c.n_fast ? c.fast_step : c.slow_step) : c.step_dist;
+        const double cx = clampd(px, c.left, c.right), cy = clampd(py, c.up, c.down);
+        gx = cx; gy = cy;
+        if (a == 0) gx = fmax(px - stp, c.left);
+        else if (a == 1) gx = fmin(px + stp, c.right);
+        else if (a == 2) gy = fmax(py - stp, c.up);
+        else if (a == 3) gy = fmin(py + stp, c.down);
+    }
+    double v = 0, om = 0, cs = 1, sn = 0, cd = 1, sd = 0, dist = 0;
+    if (c.track_dist && prev_valid && me) { const double dx = px - qx, dy = py - qy; dist = sqrt(dx * dx + dy * dy); }
+    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0;
+    const int UF = c.update_frequency;
+    for (int k = 0; k < UF; k++) {
+        if (k > 0) dist += kTimeStep * fabs(v);
+        qx = px; qy = py;
+        if (k % c.ctrl_period == 0 || c.robotarium) {
+            double xi_x = 0, xi_y = 0, ux = 0, uy = 0;
+            if (me) {
+                sincos(th, &sn, &cs);
+                xi_x = px + kProjectionDistance * cs; xi_y = py + kProjectionDistance * sn;
+                double dx = gx - xi_x, dy = gy - xi_y;
+                const double nrm = sqrt(dx * dx + dy * dy);
+                if (nrm > kSiVelocityLimit) { const double sc = kSiVelocityLimit / nrm; dx *= sc; dy *= sc; }
+                ux = dx; uy = dy;
+            }
+            const int it = qp.run(xi_x, xi_y, ux, uy, c.barrier_default != 0);
+            n_it += it; n_stall += it >= 25; n_qp++;
+            if (me) {
+                const double vv = cs * ux + sn * uy;
+                double ww = (1.0 / kProjectionDistance) * (-sn * ux + cs * uy);
+                ww = clampd(ww, -kAngularLimit, kAngularLimit);
+                v = clampd(vv, -kMaxLinearVelocity, kMaxLinearVelocity);
+                om = clampd(ww, -kMaxAngularVelocity, kMaxAngularVelocity);
+                sincos(kTimeStep * om, &sd, &cd);
+            }
+        }
+        bool viol = me && ((px < kArenaXMin) | (px > kArenaXMax) | (py < kArenaYMin) | (py > kArenaYMax));
+        const bool viol_b = __any_sync(kFull, viol);
+        bool vc = false;
+#pragma unroll
+        for (int t = 0; t < PPL; t++) {
+            const double xi_ = __shfl_sync(kFull, px, qp.pi[t]), yi_ = __shfl_sync(kFull, py, qp.pi[t]);
+            const double xj_ = __shfl_sync(kFull, px, qp.pj[t]), yj_ = __shfl_sync(kFull, py, qp.pj[t]);
+            const double dx = xi_ - xj_, dy = yi_ - yj_;
+            vc |= qp.pv[t] && (dx * dx + dy * dy) <= p.collision_thr2;
+        }
+        const bool viol_c = __any_sync(kFull, vc);
+        if (me) {
+            px = px + kTimeStep * cs * v;
+            py = py + kTimeStep * sn * v;
+            double t = th + kTimeStep * om;
+            th = t > kPi ? t - kTwoPi : (t < -kPi ? t + kTwoPi : t);
+            const double c2 = cs * cd - sn * sd;
+            sn = sn * cd + cs * sd;
+            cs = c2;
+        }
+        if (c.penalize_violations && (viol_c || viol_b)) {
+            msg = (viol_c ? 1 : 0) + (viol_b ? 2 : 0);
+            dist += kTimeStep * fabs(v);
+            break;
+        }
+    }
+
+    // ---------------------------------------------------------------- scenario tail
+    const int D = p.obs_dim;
+    float *obs = p.buf.obs + env * (int64_t)(N * D) + (int64_t)lane * D;
+    float rew = 0.f;
+    bool done = false;
+    int remaining = 0, scen_metric = 0;
+
+    // stage every robot's position in the (now idle) QP workspace so that any lane can read any
+    // robot without shuffles inside lane-dependent control flow
+    double *spx = qp.xix, *spy = qp.xiy, *sbx = qp.vx, *sby = qp.vq;
+    __syncwarp();
+    if (me) { spx[lane] = px; spy[lane] = py; }
+    __syncwarp();
+    // neighbour order shared by PCP / Warehouse: all others by index, or the K nearest (misc.py:20-25)
+    auto for_each_block = [&](auto put) {
+        put(lane);
+        if (c.num_neighbors >= N - 1) {
+            for (int b = 0; b < N; b++) if (b != lane) put(b);
+        } else {
+            uint32_t used = 1u << lane;
+            for (int kk = 0; kk < c.num_neighbors; kk++) {
+                int best = -1; double bdist = 0.0;
+                for (int b = 0; b < N; b++) {
+                    const double dx = spx[b] - px, dy = spy[b] - py, dd = dx * dx + dy * dy;
+                    if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
+                }
+                used |= 1u << best;
+                put(best);
+            }
+        }
+    };
+
+    if (SCN == MRB_PCP) {
+        const int P = c.num_prey;
+        uint32_t sensed = (uint32_t)sci[0], captured = (uint32_t)sci[S];
+        const int unseen0 = P - __popc(sensed), left0 = P - __popc(captured);
+        double bd = -1.0, bx = -5.0, by = -5.0;
+        const bool pred = lane < c.num_predators;
+        for (int q = 0; q < P; q++) {
+            if ((captured >> q) & 1) continue;
+            const double qxp = scf[(2 * q) * S], qyp = scf[(2 * q + 1) * S];
+            const double dx = px - qxp, dy = py - qyp, d2 = dx * dx + dy * dy;
+            const bool in_range = me && d2 <= (pred ? p.sense_thr2 : 0.0);
+            const bool sense = __any_sync(kFull, in_range);
+            const bool capture = __any_sync(kFull, me && act == 4 && d2 <= (pred ? 0.0 : p.capture_thr2));
+            if (sense) sensed |= 1u << q;
+            if (((sensed >> q) & 1) && capture) { captured |= 1u << q; continue; }
+            if (in_range && (bd < 0.0 || d2 < bd)) { bd = d2; bx = qxp; by = qyp; }
+        }
+        const int unseen = P - __popc(sensed), left = P - __popc(captured);
+        if (lane == 0) { sci[0] = (int32_t)sensed; sci[S] = (int32_t)captured; }
+        const int od = c.capability_aware ? 6 : 4;
+        int slot = 0;
+        if (me) { sbx[lane] = bx; sby[lane] = by; }
+        __syncwarp();
+        auto put = [&](int b) {
+            float *o = obs + slot * od;
+            o[0] = (float)spx[b]; o[1] = (float)spy[b]; o[2] = (float)sbx[b]; o[3] = (float)sby[b];
+            if (od == 6) {
+                o[4] = (float)(b < c.num_predators ? c.predator_radius : 0.0);
+                o[5] = (float)(b < c.num_predators ? 0.0 : c.capture_radius);
+            }
+            slot++;
+        };
+        if (me) for_each_block(put);
+        if (msg) { rew = (float)c.violation_reward; done = true; }
+        else {
+            rew = (float)(((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty);
+            done = steps > c.max_episode_steps || left == 0;
+        }
+        remaining = left; scen_metric = P - left;
+    } else if (SCN == MRB_WAREHOUSE) {
+        uint32_t loaded = (uint32_t)sci[0];
+        int slot = 0;
+        auto put = [&](int b) {
+            float *o = obs + slot * 3;
+            o[0] = (float)spx[b]; o[1] = (float)spy[b]; o[2] = (float)((loaded >> b) & 1);
+            slot++;
+        };
+        if (me) for_each_block(put);
+        bool set_bit = false, clr_bit = false;
+        if (msg) { rew = (float)c.violation_reward; done = true; }
+        else {
+            if (me) {
+                const bool green = (lane % 2 == 0), ld = (loaded >> lane) & 1;
+                if (ld) {
+                    if (px < -1.5 + c.goal_width && ((green && py > 0) || (!green && py <= 0))) { rew = (float)c.unload_reward; clr_bit = true; }
+                } else {
+                    if (px > 1.5 - c.goal_width && ((!green && py > 0) || (green && py <= 0))) { rew = (float)c.load_reward; set_bit = true; }
+                }
+            }
+            done = steps > c.max_episode_steps;
+        }
+        const uint32_t setm = __ballot_sync(kFull, set_bit), clrm = __ballot_sync(kFull, clr_bit);
+        loaded = (loaded | setm) & ~clrm;
+        scen_metric = __popc(clrm);
+        if (lane == 0) sci[0] = (int32_t)loaded;
+    } else if (SCN == MRB_MATERIAL) {
+        int load = me ? sci[lane * S] : 0;
+        int zone0 = sci[N * S], zone1 = sci[(N + 1) * S];
+        int messages = 0;
+        for (int i = 0; i < 4; i++) messages |= (__shfl_sync(kFull, act, i) % 4) << (2 * i);
+        if (me) {
+            float *o = obs;
+            o[0] = (float)px; o[1] = (float)py; o[2] = (float)load; o[3] = (float)zone0; o[4] = (float)zone1;
+            for (int i = 0; i < 4; i++) o[5 + i] = (float)((messages >> (2 * i)) & 3);
+            if (c.capability_aware) {
+                o[9] = (float)(lane < c.n_fast ? c.small_torque : c.large_torque);
+                o[10] = (float)(lane < c.n_fast ? c.fast_step : c.slow_step);
+            }
+        }
+        double r;
+        if (msg) { r = c.violation_reward; done = true; }
+        else {
+            r = c.time_penalty;
+            for (int a = 0; a < N; a++) {               // sequential through the shared zone loads; every lane runs it
+                const double xa = __shfl_sync(kFull, px, a), ya = __shfl_sync(kFull, py, a);
+                int la = __shfl_sync(kFull, load, a);
+                const int torque = a < c.n_fast ? c.small_torque : c.large_torque;
+                if (la > 0) {
+                    if (xa < -1.5 + c.goal_width) { r += la * c.unload_reward; scen_metric += la; la = 0; }
+                } else {
+                    int zi = -1;
+                    if (xa > 1.5 - c.goal_width) zi = 1;
+                    else if (xa * xa + ya * ya <= p.zone1_thr2) zi = 0;
+                    if (zi >= 0) {
+                        const int zl = zi ? zone1 : zone0, take = zl > torque ? torque : zl;
+                        la = take;
+                        if (zi) zone1 = zl - take; else zone0 = zl - take;
+                        r += take * c.load_reward;
+                    }
+                }
+                if (lane == a) load = la;
+            }
+            done = steps > c.max_episode_steps;
+            if (!done) done = zone0 == 0 && zone1 == 0 && !__any_sync(kFull, me && load != 0);
+        }
+        rew = (float)r;
+        int tot = load;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+        remaining = zone0 + zone1 + tot;
+        if (me) sci[lane * S] = load;
+        if (lane == 0) { sci[N * S] = zone0; sci[(N + 1) * S] = zone1; sci[(N + 2) * S] = messages; }
+    } else {                                            // Simple
+        const double goalx = scf[0], goaly = scf[S];
+        if (me) {
+            int k = 0;
+            obs[k++] = (float)px; obs[k++] = (float)py;
+            for (int b = 0; b < N; b++) if (b != lane) { obs[k++] = (float)spx[b]; obs[k++] = (float)spy[b]; }
+            obs[k] = (float)goalx; obs[k + 1] = (float)goaly;
+        }
+        const double dx = px - goalx, dy = py - goaly;
+        rew = msg ? (float)c.violation_reward : (float)(-(dx * dx + dy * dy) * c.reward_scaler);
+        done = msg != 0 || steps > c.max_episode_steps;
+    }
+
+    // ---------------------------------------------------------------- write back
+    if (me) {
+        sf[lane * S] = px; sf[(N + lane) * S] = py; sf[(2 * N + lane) * S] = th;
+        sf[(3 * N + lane) * S] = qx; sf[(4 * N + lane) * S] = qy;
+        p.buf.reward[env * N + lane] = rew;
+        if (p.buf.dist) p.buf.dist[env * N + lane] = (float)dist;
+    }
+    float team = me ? rew : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) team += __shfl_xor_sync(kFull, team, o);
+    double ep_return = 0.0;
+    if (lane == 0) {
+        si[0] = steps; si[S] = 1;
+        p.buf.done[env] = done ? 1 : 0;
+        p.buf.message[env] = (uint8_t)msg;
+        p.buf.remaining[env] = remaining;
+        ep_return = sf[(5 * N) * S] + (double)team;
+        sf[(5 * N) * S] = ep_return;
+        if (c.collect_stats && p.buf.stats) {
+            double *st = p.buf.stats;
+            atomicAdd(st + MRB_STAT_ENV_STEPS, 1.0);
+            atomicAdd(st + MRB_STAT_QP_SOLVES, (double)n_qp);
+            atomicAdd(st + MRB_STAT_QP_ITERS, (double)n_it);
+            if (n_stall) atomicAdd(st + MRB_STAT_QP_STALLS, (double)n_stall);
+            if (done) {
+                atomicAdd(st + MRB_STAT_EPISODES, 1.0);
+                atomicAdd(st + MRB_STAT_RETURN, ep_return);
+                atomicAdd(st + MRB_STAT_LENGTH, (double)steps);
+                if (msg & 1) atomicAdd(st + MRB_STAT_COLLISION, 1.0);
+                if (msg & 2) atomicAdd(st + MRB_STAT_BOUNDARY, 1.0);
+                if (!msg && steps > c.max_episode_steps) atomicAdd(st + MRB_STAT_TIMEOUTS, 1.0);
+                atomicAdd(st + MRB_STAT_SCENARIO, (double)scen_metric);
+            }
+        }
+    }
+    __syncwarp();
+    if (done && c.auto_reset && lane == 0) reset_env<SCN>(p, env);
+}
+
+inline int pairs_per_lane(int N) { return (N * (N - 1) / 2 + 31) / 32; }
+
+template <int SCN, int PPL>
+inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions, cudaStream_t s)
+{
+    const size_t smem = warp_workspace_doubles(p.cfg.num_robots) * sizeof(double) * kWarpsPerBlock;
+    cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return st;
+    const unsigned grid = (unsigned)((p.B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    step_warp_kernel<SCN, PPL><<<grid, kWarpsPerBlock * 32, smem, s>>>(p, actions);
+    return cudaSuccess;
+}
+
+template <int SCN>
+inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cudaStream_t s)
+{
+    const int ppl = pairs_per_lane(p.cfg.num_robots);
+    if (ppl <= 1) return launch_step_warp_ppl<SCN, 1>(p, actions, s);
+    if (ppl <= 2) return launch_step_warp_ppl<SCN, 2>(p, actions, s);
+    if (ppl <= 4) return launch_step_warp_ppl<SCN, 4>(p, actions, s);
+    if (ppl <= 6) return launch_step_warp_ppl<SCN, 6>(p, actions, s);
+    if (ppl <= 8) return launch_step_warp_ppl<SCN, 8>(p, actions, s);
+    return launch_step_warp_ppl<SCN, 16>(p, actions, s);
+}
+
+// ---- barrier QP alone, one problem per warp
+template <int PPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+qp_warp_kernel(int N, int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
+               double *__restrict__ u, int32_t *__restrict__ iters)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t e = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    if (e >= B) return;
+    QpWarp<PPL> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    double xx = 0, xy = 0, ux = 0, uy = 0;
+    if (lane < N) { xx = xi[lane * B + e]; xy = xi[(N + lane) * B + e]; ux = dxi[lane * B + e]; uy = dxi[(N + lane) * B + e]; }
+    const int it = qp.run(xx, xy, ux, uy, barrier_default != 0);
+    if (lane < N) { u[lane * B + e] = ux; u[(N + lane) * B + e] = uy; }
+    if (iters && lane == 0) iters[e] = it;
+}
+
+template <int PPL>
+inline cudaError_t launch_qp_warp_ppl(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
+{
+    const size_t smem = warp_workspace_doubles(N) * sizeof(double) * kWarpsPerBlock;
+    cudaError_t st = cudaFuncSetAttribute(qp_warp_kernel<PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return st;
+    qp_warp_kernel<PPL><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem, s>>>(N, B, bd, dxi, xi, u, iters);
+    return cudaSuccess;
+}
+inline cudaError_t launch_qp_warp(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
+{
+    const int ppl = pairs_per_lane(N);
+    if (ppl <= 1) return launch_qp_warp_ppl<1>(N, bd, B, dxi, xi, u, iters, s);
+    if (ppl <= 2) return launch_qp_warp_ppl<2>(N, bd, B, dxi, xi, u, iters, s);
+    if (ppl <= 4) return launch_qp_warp_ppl<4>(N, bd, B, dxi, xi, u, iters, s);
+    if (ppl <= 6) return launch_qp_warp_ppl<6>(N, bd, B, dxi, xi, u, iters, s);
+    if (ppl <= 8) return launch_qp_warp_ppl<8>(N, bd, B, dxi, xi, u, iters, s);
+    return launch_qp_warp_ppl<16>(N, bd, B, dxi, xi, u, iters, s);
+}
+
+}  // namespace mrb
