@@ -124,7 +124,7 @@ def cpu_port_rate(args, cfg, seconds, envs=None):
     import c_oracle
     cores = os.cpu_count() or 1
     orc = c_oracle.COracle(args.scenario, cfg)
-    B = envs or max(cores * 256, 4096)
+    B = envs or max(cores * 1024, 16384)
     sf, si = orc.reset_flat(B, seed=0, threads=cores)
     rng = np.random.RandomState(0)
     acts = [rng.randint(0, orc.n_actions, size=(B, orc.N)).astype(np.int32) for _ in range(8)]

@@ -286,7 +286,7 @@ def _threaded(run, B, threads):
         run(0, B)
         return
     # fine-grained chunks so that envs that early-exit do not unbalance the threads
-    chunk = max(1, B // (threads * 8))
+    chunk = max(1, min(max(256, B // (threads * 8)), -(-B // threads)))
     spans = [(lo, min(B, lo + chunk)) for lo in range(0, B, chunk)]
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(lambda s: run(*s), spans))
