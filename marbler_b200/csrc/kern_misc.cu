@@ -37,7 +37,7 @@ qp_thread_kernel(int64_t B, int barrier_default, const double *__restrict__ dxi,
         xix[i] = xi[i * B + e]; xiy[i] = xi[(N + i) * B + e];
         ux[i] = dxi[i * B + e]; uy[i] = dxi[(N + i) * B + e];
     }
-    QpThread<N> qp;
+    QpForTeam<N> qp;
     const int it = qp.run(xix, xiy, ux, uy, barrier_default != 0);
 #pragma unroll
     for (int i = 0; i < N; i++) { u[i * B + e] = ux[i]; u[(N + i) * B + e] = uy[i]; }

@@ -8,10 +8,16 @@
 #pragma once
 #include "common.cuh"
 #include "qp_thread.cuh"
+#include "qp_dual.cuh"
+#include <type_traits>
 
 namespace mrb {
 
 constexpr int kThreadsPerBlock = 64;
+
+// up to 4 robots the constraint-space (dual) Newton system is the smaller one (m <= 6 < 2N)
+template <int N>
+using QpForTeam = std::conditional_t<(N >= 2 && N <= 4), QpDual<N>, QpThread<N>>;
 
 // every scenario's Agent.generate_goal: PredatorCapturePrey/agent.py:48-76, warehouse.py:19-45,
 // MaterialTransport.py:19-46, ArcticTransport/agent.py:114-137, simple.py:32-60
@@ -228,7 +234,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                 }
                 ux[i] = dx; uy[i] = dy;
             }
-            QpThread<N> qp;
+            QpForTeam<N> qp;
             const int it = qp.run(xix, xiy, ux, uy, c.barrier_default != 0);   // controller.py:23
             n_it += it;
             n_stall += it >= 25;
