@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "../../include/marbler_b200.h"
 
 namespace mrb {
@@ -100,6 +101,18 @@ struct Philox {
         return sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);
     }
 };
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E).  nvcc's `#pragma unroll` gives up
+// on triangular loop nests (it leaves a runtime loop and the factor lands in local memory); with the
+// outer index a template constant every inner bound is a literal and unrolls reliably.
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 

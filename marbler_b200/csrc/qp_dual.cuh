@@ -38,50 +38,59 @@ struct QpDual {
     static constexpr int m = N * (N - 1) / 2;
     static constexpr int MT = m * (m + 1) / 2;
     __device__ static constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }   // r >= c
-    // pair index -> robots (compile-time after unrolling)
-    __device__ static constexpr int pair_i(int c) { int i = 0, rem = c; while (rem >= N - 1 - i) { rem -= N - 1 - i; i++; } return i; }
-    __device__ static constexpr int pair_j(int c) { int i = 0, rem = c; while (rem >= N - 1 - i) { rem -= N - 1 - i; i++; } return i + 1 + rem; }
 
     double ax[m], ay[m], h[m];
     double L[MT], invd[m];
 
     __device__ __forceinline__ void G_mul(const double (&v)[n], double (&out)[m]) const
     {
+        int c = 0;
 #pragma unroll
-        for (int c = 0; c < m; c++) {
-            const int i = pair_i(c), j = pair_j(c);
-            out[c] = ax[c] * (v[2 * j] - v[2 * i]) + ay[c] * (v[2 * j + 1] - v[2 * i + 1]);
-        }
+        for (int i = 0; i < N - 1; i++)
+#pragma unroll
+            for (int j = i + 1; j < N; j++, c++)
+                out[c] = ax[c] * (v[2 * j] - v[2 * i]) + ay[c] * (v[2 * j + 1] - v[2 * i + 1]);
     }
     __device__ __forceinline__ void GT_acc(const double (&y)[m], double (&out)[n]) const
     {
+        int c = 0;
 #pragma unroll
-        for (int c = 0; c < m; c++) {
-            const int i = pair_i(c), j = pair_j(c);
-            const double tx = ax[c] * y[c], ty = ay[c] * y[c];
-            out[2 * i] -= tx; out[2 * i + 1] -= ty;
-            out[2 * j] += tx; out[2 * j + 1] += ty;
-        }
+        for (int i = 0; i < N - 1; i++)
+#pragma unroll
+            for (int j = i + 1; j < N; j++, c++) {
+                const double tx = ax[c] * y[c], ty = ay[c] * y[c];
+                out[2 * i] -= tx; out[2 * i + 1] -= ty;
+                out[2 * j] += tx; out[2 * j + 1] += ty;
+            }
     }
     // L := chol(1/2 G G' + diag(d))
     __device__ __forceinline__ void factor(const double (&d)[m])
     {
+        {
+            int c = 0;
 #pragma unroll
-        for (int c = 0; c < m; c++) {
-            L[tri(c, c)] = fma(ax[c], ax[c], ay[c] * ay[c]) + d[c];      // 1/2 |g_c|^2 = |a_c|^2
+            for (int i = 0; i < N - 1; i++)
 #pragma unroll
-            for (int e = 0; e < c; e++) {
-                const int i = pair_i(c), j = pair_j(c), k = pair_i(e), l = pair_j(e);
-                const int sgn = (i == k) + (j == l) - (i == l) - (j == k);
-                if (sgn == 0) L[tri(c, e)] = 0.0;
-                else {
-                    const double dot = fma(ax[c], ax[e], ay[c] * ay[e]);
-                    L[tri(c, e)] = sgn > 0 ? 0.5 * dot : -0.5 * dot;
+                for (int j = i + 1; j < N; j++, c++) {
+                    L[tri(c, c)] = fma(ax[c], ax[c], ay[c] * ay[c]) + d[c];      // 1/2 |g_c|^2 = |a_c|^2
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < N - 1; k++)
+#pragma unroll
+                        for (int l = k + 1; l < N; l++, e++) {
+                            if (e < c) {
+                                const int sgn = (i == k) + (j == l) - (i == l) - (j == k);
+                                if (sgn == 0) L[tri(c, e)] = 0.0;
+                                else {
+                                    const double dot = fma(ax[c], ax[e], ay[c] * ay[e]);
+                                    L[tri(c, e)] = sgn > 0 ? 0.5 * dot : -0.5 * dot;
+                                }
+                            }
+                        }
                 }
-            }
         }
-#pragma unroll
-        for (int j = 0; j < m; j++) {
+        static_for<0, m>([&](auto J) {
+            constexpr int j = decltype(J)::value;
             double dj = L[tri(j, j)];
 #pragma unroll
             for (int k = 0; k < j; k++) dj = fma(-L[tri(j, k)], L[tri(j, k)], dj);
@@ -94,24 +103,24 @@ struct QpDual {
                 for (int k = 0; k < j; k++) v = fma(-L[tri(i, k)], L[tri(j, k)], v);
                 L[tri(i, j)] = v * r;
             }
-        }
+        });
     }
     __device__ __forceinline__ void solve(double (&b)[m]) const
     {
-#pragma unroll
-        for (int i = 0; i < m; i++) {
+        static_for<0, m>([&](auto I) {
+            constexpr int i = decltype(I)::value;
             double v = b[i];
 #pragma unroll
             for (int k = 0; k < i; k++) v = fma(-L[tri(i, k)], b[k], v);
             b[i] = v * invd[i];
-        }
-#pragma unroll
-        for (int i = m - 1; i >= 0; i--) {
+        });
+        static_for<0, m>([&](auto I) {
+            constexpr int i = m - 1 - decltype(I)::value;
             double v = b[i];
 #pragma unroll
             for (int k = i + 1; k < m; k++) v = fma(-L[tri(k, i)], b[k], v);
             b[i] = v * invd[i];
-        }
+        });
     }
 
     __device__ __forceinline__ int run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N],
@@ -130,19 +139,24 @@ struct QpDual {
         }
         const double r2 = barrier_default ? 0.17 * 0.17 : 0.2 * 0.2;
         double hh = 0.0, qq = 0.0;
+        {
+            int c = 0;
 #pragma unroll
-        for (int c = 0; c < m; c++) {
-            const int i = pair_i(c), j = pair_j(c);
-            const double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
-            const double hv = (ex * ex + ey * ey) - r2;
-            const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
-            h[c] = gain * (hv * hv * hv);
-            ax[c] = 2.0 * ex; ay[c] = 2.0 * ey;
-            hh = fma(h[c], h[c], hh);
+            for (int i = 0; i < N - 1; i++)
+#pragma unroll
+                for (int j = i + 1; j < N; j++, c++) {
+                    const double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
+                    const double hv = (ex * ex + ey * ey) - r2;
+                    const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
+                    h[c] = gain * (hv * hv * hv);
+                    ax[c] = 2.0 * ex; ay[c] = 2.0 * ey;
+                    hh = fma(h[c], h[c], hh);
+                }
         }
 #pragma unroll
         for (int a = 0; a < n; a++) qq = fma(q[a], q[a], qq);
-        const double resx0 = fmax(1.0, sqrt(qq)), resz0 = fmax(1.0, sqrt(hh));
+        // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2
+        const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
 
         double s[m], z[m], t1[m], t2[m];
         // ---- default starting point [P G'; G -I][x; z] = [-q; h]:  (1/2 GG' + I) z = -h - 1/2 G q,  x = -1/2 (q + G'z)
@@ -204,12 +218,12 @@ struct QpDual {
                 zrz = fma(z[c], rz[c], zrz);
             }
             const double pcost = f0, dcost = f0 + zrz - gap;
-            // relgap <= reltol without the division: gap <= 1e-2 * denominator (denominator > 0)
+            // cvxopt's stopping rule without sqrt / division: relgap <= reltol  <=>  gap <= 1e-2 * denominator,
+            // pres = sqrt(resz)/resz0 <= feastol  <=>  resz <= (1e-2 * resz0)^2   (equal up to 1 ulp at the threshold)
             bool gap_ok = gap <= 1e-7;
-            if (pcost < 0.0) gap_ok = gap_ok || (gap / -pcost <= 1e-2);
-            else if (dcost > 0.0) gap_ok = gap_ok || (gap / dcost <= 1e-2);
-            const double pres = sqrt(resz) / resz0, dres = sqrt(resx) / resx0;
-            if ((pres <= 1e-2 && dres <= 1e-2 && gap_ok) || iters == 50) break;
+            if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
+            else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
+            if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
 
             double zinv[m], sinv[m], dz[m], ds[m];
 #pragma unroll
@@ -236,8 +250,8 @@ struct QpDual {
                 tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
                 ds[c] = p;                                    // keep only the Mehrotra correction term
             }
-            double step = tmax == 0.0 ? 1.0 : fmin(1.0, 1.0 / tmax);
-            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz / gap * (step * step)));
+            double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);          // t == 0 ? 1 : min(1, 1/t)
+            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
             const double sigmamu = sg * sg * sg * (gap / m);
             // corrector (rc = -s.z - ds_aff.dz_aff + sigma mu)
             double corr[m];
@@ -253,7 +267,7 @@ struct QpDual {
                 ds[c] = corr[c] - s[c] - t1[c] * dz[c];
                 tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
             }
-            step = tmax == 0.0 ? 1.0 : fmin(1.0, 0.99 / tmax);
+            step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);          // t == 0 ? 1 : min(1, 0.99/t)
             // dx = -1/2 (rx + G'dz)
             GT_acc(dz, rx);
             const double hstep = -0.5 * step;

@@ -69,8 +69,8 @@ struct QpThread {
                 L[tri(2 * j, 2 * i)] -= pxx; L[tri(2 * j, 2 * i + 1)] -= pxy;
                 L[tri(2 * j + 1, 2 * i)] -= pxy; L[tri(2 * j + 1, 2 * i + 1)] -= pyy;
             }
-#pragma unroll
-        for (int j = 0; j < n; j++) {
+        static_for<0, n>([&](auto J) {
+            constexpr int j = decltype(J)::value;
             double d = L[tri(j, j)];
 #pragma unroll
             for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
@@ -84,24 +84,24 @@ struct QpThread {
                 for (int k = 0; k < j; k++) v -= L[tri(i, k)] * L[tri(j, k)];
                 L[tri(i, j)] = v * r;
             }
-        }
+        });
     }
     __device__ __forceinline__ void solve(double (&b)[n]) const
     {
-#pragma unroll
-        for (int i = 0; i < n; i++) {
+        static_for<0, n>([&](auto I) {
+            constexpr int i = decltype(I)::value;
             double v = b[i];
 #pragma unroll
             for (int k = 0; k < i; k++) v -= L[tri(i, k)] * b[k];
             b[i] = v * invd[i];
-        }
-#pragma unroll
-        for (int i = n - 1; i >= 0; i--) {
+        });
+        static_for<0, n>([&](auto I) {
+            constexpr int i = n - 1 - decltype(I)::value;
             double v = b[i];
 #pragma unroll
             for (int k = i + 1; k < n; k++) v -= L[tri(k, i)] * b[k];
             b[i] = v * invd[i];
-        }
+        });
     }
 
     // xi: SI points; u: in = nominal dxi (already norm-limited to 0.15 by the position controller),

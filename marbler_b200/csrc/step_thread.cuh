@@ -14,6 +14,9 @@
 namespace mrb {
 
 constexpr int kThreadsPerBlock = 64;
+#ifndef MRB_MIN_BLOCKS
+#define MRB_MIN_BLOCKS 4
+#endif
 
 // up to 4 robots the constraint-space (dual) Newton system is the smaller one (m <= 6 < 2N)
 template <int N>
@@ -157,7 +160,7 @@ __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *ma
 
 // ---- the step
 template <int SCN, int N>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, MRB_MIN_BLOCKS)
 step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
     const int64_t env = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# scratch: build a library variant with extra -D flags:  scripts/build_variant.sh <suffix> <nvcc flags...>
+set -e
+cd "$(dirname "$0")/../marbler_b200"
+suffix=$1; shift
+mkdir -p build/$suffix
+for f in csrc/*.cu; do
+  b=$(basename $f .cu)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c -o build/$suffix/$b.o $f &
+done
+wait
+nvcc -shared -o libmarbler_b200_$suffix.so build/$suffix/*.o
+echo built libmarbler_b200_$suffix.so
