@@ -34,7 +34,7 @@ METRIC = "batched env-steps/s (PredatorCapturePrey-v0, barrier certs on)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenario", default="PredatorCapturePrey")
