@@ -112,8 +112,10 @@ int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void *cuda_strea
  * (roboEnv.py:38-96) -> Controller.set_velocities (controller.py:20-25) -> rps / cvxopt.
  * actions: device i32 [B][N]. */
 int mrb_step(mrb_env *env, const int32_t *actions, void *cuda_stream);
-/* same step with HOST buffers (pinned or pageable): H2D actions, step, D2H obs/reward/done/message,
- * then synchronises the stream.  NULL host outputs are skipped. */
+/* same step with HOST buffers (pinned for full speed; pageable works): H2D actions, step, D2H
+ * obs/reward/done/message, then synchronises.  Batches of >= 16,384 envs are cut into chunks that
+ * alternate over two library-internal streams (ordered after the caller's stream) so that the PCIe
+ * copies of one chunk overlap the kernel of the next.  NULL host outputs are skipped. */
 int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                   uint8_t *done_host, uint8_t *message_host, void *cuda_stream);
 /* unit entry for the barrier-certificate QP alone (rps create_single_integrator_barrier_certificate{,2}

@@ -17,6 +17,9 @@ struct mrb_env {
     int device;
     bool bound;
     int32_t *actions_dev;       // staging for mrb_step_host
+    cudaStream_t pipe[2];       // internal streams of the chunked host path
+    cudaEvent_t ev_in, ev_out[2];
+    bool pipe_ready;
     std::string err;
 };
 
@@ -108,6 +111,8 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
     std::memset(&e->p, 0, sizeof(Params));
     e->p.cfg = c;
     e->p.B = num_envs;
+    e->p.env_lo = 0;
+    e->p.env_hi = num_envs;
     e->p.env_id0 = env_id0;
     e->p.seed = 0;
     e->p.obs_dim = obs_dim_of(c);
@@ -121,6 +126,7 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
     e->device = device;
     e->bound = false;
     e->actions_dev = nullptr;
+    e->pipe_ready = false;
     *out = e;
     return MRB_OK;
 }
@@ -128,7 +134,12 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
 extern "C" int mrb_destroy(mrb_env *env)
 {
     if (!env) return MRB_E_ARG;
-    if (env->actions_dev) { cudaSetDevice(env->device); cudaFree(env->actions_dev); }
+    cudaSetDevice(env->device);
+    if (env->actions_dev) cudaFree(env->actions_dev);
+    if (env->pipe_ready) {
+        for (int k = 0; k < 2; k++) { cudaStreamDestroy(env->pipe[k]); cudaEventDestroy(env->ev_out[k]); }
+        cudaEventDestroy(env->ev_in);
+    }
     delete env;
     return MRB_OK;
 }
@@ -173,22 +184,21 @@ extern "C" int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void 
     return MRB_OK;
 }
 
-extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
+// launch the step kernel for envs [lo, hi) on stream s
+static int step_range(mrb_env *env, const int32_t *actions, int64_t lo, int64_t hi, cudaStream_t s)
 {
-    if (!env || !actions) return MRB_E_ARG;
-    if (!env->bound) return fail(env, MRB_E_STATE, "mrb_step: call mrb_bind first");
-    if ((uintptr_t)actions & 15) return fail(env, MRB_E_ARG, "mrb_step: actions must be 16-byte aligned");
-    cudaError_t st = cudaSetDevice(env->device);
-    if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
-    cudaStream_t s = (cudaStream_t)stream;
-    // teams of up to kMaxThreadRobots robots: one env per thread (registers); larger teams: one env per warp
+    Params p = env->p;
+    p.env_lo = lo;
+    p.env_hi = hi;
+    // teams of up to 6 robots: one env per thread (registers); larger teams: one env per warp
     bool launched = false;
-    switch (env->p.cfg.scenario) {
-    case MRB_PCP: st = launch_step_pcp(env->p, actions, s, &launched); break;
-    case MRB_WAREHOUSE: st = launch_step_warehouse(env->p, actions, s, &launched); break;
-    case MRB_MATERIAL: st = launch_step_material(env->p, actions, s, &launched); break;
-    case MRB_ARCTIC: st = launch_step_arctic(env->p, actions, s, &launched); break;
-    default: st = launch_step_simple(env->p, actions, s, &launched); break;
+    cudaError_t st;
+    switch (p.cfg.scenario) {
+    case MRB_PCP: st = launch_step_pcp(p, actions, s, &launched); break;
+    case MRB_WAREHOUSE: st = launch_step_warehouse(p, actions, s, &launched); break;
+    case MRB_MATERIAL: st = launch_step_material(p, actions, s, &launched); break;
+    case MRB_ARCTIC: st = launch_step_arctic(p, actions, s, &launched); break;
+    default: st = launch_step_simple(p, actions, s, &launched); break;
     }
     if (st != cudaSuccess) return cuda_fail(env, st, "step kernel launch");
     if (!launched) return fail(env, MRB_E_UNSUPPORTED, "mrb_step: no kernel for this (scenario, num_robots)");
@@ -197,6 +207,20 @@ extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
     return MRB_OK;
 }
 
+extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
+{
+    if (!env || !actions) return MRB_E_ARG;
+    if (!env->bound) return fail(env, MRB_E_STATE, "mrb_step: call mrb_bind first");
+    if ((uintptr_t)actions & 15) return fail(env, MRB_E_ARG, "mrb_step: actions must be 16-byte aligned");
+    cudaError_t st = cudaSetDevice(env->device);
+    if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
+    return step_range(env, actions, 0, env->p.B, (cudaStream_t)stream);
+}
+
+// Host-buffer step.  Large batches are cut into chunks that ping-pong over two internal streams, so that
+// the device->host copy of chunk k (the PCIe-bound part: obs is 4*N*D bytes per env) overlaps the kernel
+// of chunk k+1 and the host->device copy of its actions.  Ordered after everything already enqueued on
+// the caller's stream; synchronises before returning.
 extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                              uint8_t *done_host, uint8_t *message_host, void *stream)
 {
@@ -208,19 +232,44 @@ extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *o
     const int64_t B = env->p.B, N = env->p.cfg.num_robots, D = env->p.obs_dim;
     if (!env->actions_dev && (st = cudaMalloc(&env->actions_dev, sizeof(int32_t) * B * N)) != cudaSuccess)
         return cuda_fail(env, st, "cudaMalloc(actions staging)");
-    if ((st = cudaMemcpyAsync(env->actions_dev, actions_host, sizeof(int32_t) * B * N, cudaMemcpyHostToDevice, s)) != cudaSuccess)
-        return cuda_fail(env, st, "H2D actions");
-    const int rc = mrb_step(env, env->actions_dev, stream);
-    if (rc != MRB_OK) return rc;
+    if (!env->pipe_ready) {
+        for (int k = 0; k < 2; k++) {
+            if ((st = cudaStreamCreateWithFlags(&env->pipe[k], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamCreate");
+            if ((st = cudaEventCreateWithFlags(&env->ev_out[k], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(env, st, "cudaEventCreate");
+        }
+        if ((st = cudaEventCreateWithFlags(&env->ev_in, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(env, st, "cudaEventCreate");
+        env->pipe_ready = true;
+    }
+    // chunk size: multiple of 4 envs keeps every chunk's actions 16-byte aligned; >= 8192 envs per chunk
+    int64_t nchunks = B / 8192;
+    nchunks = nchunks < 1 ? 1 : (nchunks > 8 ? 8 : nchunks);
+    int64_t chunk = (B + nchunks - 1) / nchunks;
+    chunk = (chunk + 63) / 64 * 64;
+    if ((st = cudaEventRecord(env->ev_in, s)) != cudaSuccess) return cuda_fail(env, st, "cudaEventRecord");
+    for (int k = 0; k < 2; k++)
+        if ((st = cudaStreamWaitEvent(env->pipe[k], env->ev_in, 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
     const mrb_buffers &b = env->p.buf;
-    if (obs_host && (st = cudaMemcpyAsync(obs_host, b.obs, sizeof(float) * B * N * D, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-        return cuda_fail(env, st, "D2H obs");
-    if (reward_host && (st = cudaMemcpyAsync(reward_host, b.reward, sizeof(float) * B * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-        return cuda_fail(env, st, "D2H reward");
-    if (done_host && (st = cudaMemcpyAsync(done_host, b.done, (size_t)B, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-        return cuda_fail(env, st, "D2H done");
-    if (message_host && (st = cudaMemcpyAsync(message_host, b.message, (size_t)B, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-        return cuda_fail(env, st, "D2H message");
+    int k = 0;
+    for (int64_t lo = 0; lo < B; lo += chunk, k ^= 1) {
+        const int64_t hi = lo + chunk < B ? lo + chunk : B, n = hi - lo;
+        cudaStream_t ps = env->pipe[k];
+        if ((st = cudaMemcpyAsync(env->actions_dev + lo * N, actions_host + lo * N, sizeof(int32_t) * n * N, cudaMemcpyHostToDevice, ps)) != cudaSuccess)
+            return cuda_fail(env, st, "H2D actions");
+        const int rc = step_range(env, env->actions_dev, lo, hi, ps);
+        if (rc != MRB_OK) return rc;
+        if (obs_host && (st = cudaMemcpyAsync(obs_host + lo * N * D, b.obs + lo * N * D, sizeof(float) * n * N * D, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
+            return cuda_fail(env, st, "D2H obs");
+        if (reward_host && (st = cudaMemcpyAsync(reward_host + lo * N, b.reward + lo * N, sizeof(float) * n * N, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
+            return cuda_fail(env, st, "D2H reward");
+        if (done_host && (st = cudaMemcpyAsync(done_host + lo, b.done + lo, (size_t)n, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
+            return cuda_fail(env, st, "D2H done");
+        if (message_host && (st = cudaMemcpyAsync(message_host + lo, b.message + lo, (size_t)n, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
+            return cuda_fail(env, st, "D2H message");
+    }
+    for (int q = 0; q < 2; q++) {
+        if ((st = cudaEventRecord(env->ev_out[q], env->pipe[q])) != cudaSuccess) return cuda_fail(env, st, "cudaEventRecord");
+        if ((st = cudaStreamWaitEvent(s, env->ev_out[q], 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
+    }
     if ((st = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(env, st, "mrb_step_host sync");
     return MRB_OK;
 }

@@ -26,7 +26,8 @@ constexpr double kTwoPi = 6.28318530717958647692;
 struct Params {
     mrb_config cfg;
     mrb_buffers buf;
-    int64_t B;          // envs on this device
+    int64_t B;          // envs on this device (row stride of the state arrays)
+    int64_t env_lo, env_hi;   // this launch processes envs [env_lo, env_hi)
     int64_t env_id0;    // global id of env 0 (RNG stream offset of this rank)
     uint64_t seed;
     int32_t obs_dim;    // D

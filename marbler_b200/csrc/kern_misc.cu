@@ -9,7 +9,7 @@ template <int SCN>
 static cudaError_t launch_reset_scn(const Params &p, const uint8_t *mask, cudaStream_t s)
 {
     const int tpb = 128;
-    reset_kernel<SCN><<<(unsigned)((p.B + tpb - 1) / tpb), tpb, 0, s>>>(p, mask);
+    reset_kernel<SCN><<<(unsigned)((p.env_hi - p.env_lo + tpb - 1) / tpb), tpb, 0, s>>>(p, mask);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,15 @@ __device__ __forceinline__ double fast_rcp(double x)
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
+// one Newton step only: relative error ~2^-46 (1.4e-14).  Used where the value only scales a Newton
+// direction or a step length (the iteration recomputes its residuals, so this does not accumulate).
+__device__ __forceinline__ double fast_rcp1(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
     double r;
@@ -105,6 +114,7 @@ struct QpDual {
             }
         });
     }
+    // b := (L L')^-1 b
     __device__ __forceinline__ void solve(double (&b)[m]) const
     {
         static_for<0, m>([&](auto I) {
@@ -228,8 +238,8 @@ struct QpDual {
             double zinv[m], sinv[m], dz[m], ds[m];
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                zinv[c] = fast_rcp(z[c]);
-                sinv[c] = fast_rcp(s[c]);
+                zinv[c] = fast_rcp1(z[c]);
+                sinv[c] = fast_rcp1(s[c]);
                 t1[c] = s[c] * zinv[c];                     // D = s/z
             }
             factor(t1);

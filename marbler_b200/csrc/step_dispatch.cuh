@@ -9,7 +9,7 @@ namespace mrb {
 template <int SCN, int N>
 inline cudaError_t launch_thread(const Params &p, const int32_t *actions, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)((p.B + kThreadsPerBlock - 1) / kThreadsPerBlock);
+    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + kThreadsPerBlock - 1) / kThreadsPerBlock);
     step_thread_kernel<SCN, N><<<grid, kThreadsPerBlock, 0, s>>>(p, actions);
     return cudaGetLastError();
 }

@@ -148,8 +148,8 @@ __device__ void reset_env(const Params &p, int64_t env)
 template <int SCN>
 __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *mask)
 {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= p.B) return;
+    const int64_t env = p.env_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.env_hi) return;
     if (mask && !mask[env]) return;
     reset_env<SCN>(p, env);
     // the reference returns an all-zero observation from reset (e.g. PredatorCapturePrey.py:136)
@@ -163,8 +163,8 @@ template <int SCN, int N>
 __global__ void __launch_bounds__(kThreadsPerBlock, MRB_MIN_BLOCKS)
 step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
-    const int64_t env = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
-    if (env >= p.B) return;
+    const int64_t env = p.env_lo + (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
+    if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
     const int64_t S = p.B;
     double *sf = p.buf.state_f64 + env;

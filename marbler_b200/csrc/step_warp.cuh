@@ -332,8 +332,8 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t env = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
-    if (env >= p.B) return;
+    const int64_t env = p.env_lo + (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
     const int N = c.num_robots;
     const int64_t S = p.B;
@@ -624,7 +624,7 @@ inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions,
     const size_t smem = warp_workspace_doubles(p.cfg.num_robots) * sizeof(double) * kWarpsPerBlock;
     cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
-    const unsigned grid = (unsigned)((p.B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
     step_warp_kernel<SCN, PPL><<<grid, kWarpsPerBlock * 32, smem, s>>>(p, actions);
     return cudaSuccess;
 }

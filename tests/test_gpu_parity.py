@@ -83,8 +83,7 @@ def _resync(env, orc, sf, si, idx):
     env.state_i32[:, ti] = torch.from_numpy(pi).to(env.device)
 
 
-@pytest.mark.parametrize("scenario,B", SCN_B)
-def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
+def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
     """Same reset (same Philox draws), same random actions, T steps: the CUDA env and the C oracle must
     agree at every step (discrete bit-exact, poses 1e-5), including across auto-resets.
 
@@ -94,10 +93,10 @@ def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
     the returned iterate are not reproducible between ANY two implementations (the C oracle and the
     Python restatement disagree with each other there too).  Such env-steps (oracle reports a solve of
     >= 25 iterations; ~2e-6 of solves) are excluded and the env is re-synchronised."""
-    g = gu.Golden(scenario + "_rollout")
-    T = 40
-    env = _vec(scenario, g.cfg, B, seed=5, auto_reset=True)
-    orc = oracle_lib.COracle(scenario, g.cfg)
+    cfg = dict(gu.Golden(scenario + "_rollout").cfg)
+    cfg.update(overrides or {})
+    env = _vec(scenario, cfg, B, seed=5, auto_reset=True)
+    orc = oracle_lib.COracle(scenario, cfg)
     env.reset()
     sf, si = orc.reset_flat(B, seed=5, threads=8)
     rng = np.random.RandomState(0)
@@ -136,13 +135,42 @@ def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
         n_done += int(out_i[ok, 1].sum())
         n_msg += int((out_i[ok, 0] != 0).sum())
     stats = env.read_stats()
-    # MaterialTransport spawns every robot in ONE column (1 x 6 grid, heading 0), i.e. exactly the symmetric
-    # layout of the limit cycle, so it sees far more of them than the other scenarios
-    assert n_stalled <= max(2, int((5e-3 if scenario == "MaterialTransport" else 1e-4) * B * T)), n_stalled
+    assert n_stalled <= max(2, int(stall_frac * B * T)), n_stalled
     assert n_loose <= max(2, int(1e-4 * B * T)), n_loose
     assert abs(stats["episodes"] - n_done) <= n_stalled and stats["env_steps"] == B * T
     assert stats["collisions"] + stats["boundary_exits"] >= n_msg - n_stalled
     assert stats["qp_stalls"] <= 4 * max(n_stalled, 1)
+    return n_stalled, n_loose
+
+
+@pytest.mark.parametrize("scenario,B", SCN_B)
+def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
+    # MaterialTransport spawns every robot in ONE column (1 x 6 grid, heading 0), i.e. exactly the symmetric
+    # layout of the limit cycle, so it sees far more of them than the other scenarios
+    _lockstep(oracle_lib, scenario, B, 40, stall_frac=5e-3 if scenario == "MaterialTransport" else 1e-4)
+
+
+TEAM_CASES = [
+    ("PredatorCapturePrey", dict(predator=1, capture=1, num_neighbors=1)),                       # N=2 thread kernel
+    ("PredatorCapturePrey", dict(predator=2, capture=1, num_neighbors=1, num_prey=9)),           # N=3, K nearest
+    ("PredatorCapturePrey", dict(predator=3, capture=2, num_neighbors=4, capability_aware=True)),  # N=5 (primal QP)
+    ("PredatorCapturePrey", dict(predator=4, capture=4, num_neighbors=2, ROBOT_INIT_RIGHT_THRESH=0.1)),  # N=8 warp kernel
+    ("Simple", dict(n_agents=3)),
+    ("Simple", dict(n_agents=10, ROBOT_INIT_RIGHT_THRESH=0.1)),                                  # warp kernel
+    ("Warehouse", dict(n_agents=4, num_neighbors=3)),
+    ("Warehouse", dict(n_agents=9, num_neighbors=3)),                                            # warp kernel, K nearest
+    ("MaterialTransport", dict(n_agents=5, n_fast_agents=2, n_slow_agents=3, capability_aware=True)),
+    ("PredatorCapturePrey", dict(robotarium=True, update_frequency=10)),                         # controller every sub-step
+    ("PredatorCapturePrey", dict(barrier_certificate="default")),
+    ("Warehouse", dict(penalize_violations=False)),
+]
+
+
+@pytest.mark.parametrize("scenario,overrides", TEAM_CASES, ids=lambda v: v if isinstance(v, str) else "-".join("%s=%s" % kv for kv in sorted(v.items()))[:60])
+def test_other_team_sizes_and_options_lockstep(oracle_lib, scenario, overrides):
+    """Team sizes / options the reference fixtures do not cover, against the C oracle (which is pinned to the
+    reference for N = 4, 6, 20): every kernel dispatch path (thread N = 2..6, warp N = 7..32)."""
+    _lockstep(oracle_lib, scenario, 1024, 25, overrides=overrides, stall_frac=2e-2)
 
 
 @pytest.mark.parametrize("scenario", [s for s, _ in SCN_B])
