@@ -12,13 +12,15 @@
 
 using namespace mrb;
 
+constexpr int kPipeStreams = 8;
+
 struct mrb_env {
     Params p;
     int device;
     bool bound;
     int32_t *actions_dev;       // staging for mrb_step_host
-    cudaStream_t pipe[2];       // internal streams of the chunked host path
-    cudaEvent_t ev_in, ev_out[2];
+    cudaStream_t pipe[kPipeStreams];   // internal streams of the chunked host path (one per chunk)
+    cudaEvent_t ev_in, ev_out[kPipeStreams];
     bool pipe_ready;
     std::string err;
 };
@@ -137,7 +139,7 @@ extern "C" int mrb_destroy(mrb_env *env)
     cudaSetDevice(env->device);
     if (env->actions_dev) cudaFree(env->actions_dev);
     if (env->pipe_ready) {
-        for (int k = 0; k < 2; k++) { cudaStreamDestroy(env->pipe[k]); cudaEventDestroy(env->ev_out[k]); }
+        for (int k = 0; k < kPipeStreams; k++) { cudaStreamDestroy(env->pipe[k]); cudaEventDestroy(env->ev_out[k]); }
         cudaEventDestroy(env->ev_in);
     }
     delete env;
@@ -217,10 +219,12 @@ extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
     return step_range(env, actions, 0, env->p.B, (cudaStream_t)stream);
 }
 
-// Host-buffer step.  Large batches are cut into chunks that ping-pong over two internal streams, so that
-// the device->host copy of chunk k (the PCIe-bound part: obs is 4*N*D bytes per env) overlaps the kernel
-// of chunk k+1 and the host->device copy of its actions.  Ordered after everything already enqueued on
-// the caller's stream; synchronises before returning.
+// Host-buffer step.  Large batches are cut into up to 8 chunks, each on its own internal stream: all the
+// (small) action uploads and all the chunk kernels are enqueued at once, so the kernels of several chunks
+// share the SMs (a chunk of 8,192 envs fills a quarter of the machine and takes the same ~0.1 ms as a full
+// wave) while the device->host copies - the PCIe-bound part: obs is 4*N*D bytes per env - drain chunk after
+// chunk behind them on the copy engine.  Ordered after everything already enqueued on the caller's stream;
+// synchronises before returning.
 extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                              uint8_t *done_host, uint8_t *message_host, void *stream)
 {
@@ -233,30 +237,35 @@ extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *o
     if (!env->actions_dev && (st = cudaMalloc(&env->actions_dev, sizeof(int32_t) * B * N)) != cudaSuccess)
         return cuda_fail(env, st, "cudaMalloc(actions staging)");
     if (!env->pipe_ready) {
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kPipeStreams; k++) {
             if ((st = cudaStreamCreateWithFlags(&env->pipe[k], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamCreate");
             if ((st = cudaEventCreateWithFlags(&env->ev_out[k], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(env, st, "cudaEventCreate");
         }
         if ((st = cudaEventCreateWithFlags(&env->ev_in, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(env, st, "cudaEventCreate");
         env->pipe_ready = true;
     }
-    // chunk size: multiple of 4 envs keeps every chunk's actions 16-byte aligned; >= 8192 envs per chunk
+    // chunk size: multiple of 64 envs keeps every chunk's actions 16-byte aligned; >= 8192 envs per chunk
     int64_t nchunks = B / 8192;
-    nchunks = nchunks < 1 ? 1 : (nchunks > 8 ? 8 : nchunks);
+    nchunks = nchunks < 1 ? 1 : (nchunks > kPipeStreams ? kPipeStreams : nchunks);
     int64_t chunk = (B + nchunks - 1) / nchunks;
     chunk = (chunk + 63) / 64 * 64;
     if ((st = cudaEventRecord(env->ev_in, s)) != cudaSuccess) return cuda_fail(env, st, "cudaEventRecord");
-    for (int k = 0; k < 2; k++)
-        if ((st = cudaStreamWaitEvent(env->pipe[k], env->ev_in, 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
     const mrb_buffers &b = env->p.buf;
-    int k = 0;
-    for (int64_t lo = 0; lo < B; lo += chunk, k ^= 1) {
+    int used = 0;
+    // pass 1: uploads + kernels of every chunk; pass 2: the downloads, in chunk order
+    for (int64_t lo = 0; lo < B; lo += chunk, used++) {
         const int64_t hi = lo + chunk < B ? lo + chunk : B, n = hi - lo;
-        cudaStream_t ps = env->pipe[k];
+        cudaStream_t ps = env->pipe[used];
+        if ((st = cudaStreamWaitEvent(ps, env->ev_in, 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
         if ((st = cudaMemcpyAsync(env->actions_dev + lo * N, actions_host + lo * N, sizeof(int32_t) * n * N, cudaMemcpyHostToDevice, ps)) != cudaSuccess)
             return cuda_fail(env, st, "H2D actions");
         const int rc = step_range(env, env->actions_dev, lo, hi, ps);
         if (rc != MRB_OK) return rc;
+    }
+    int k = 0;
+    for (int64_t lo = 0; lo < B; lo += chunk, k++) {
+        const int64_t hi = lo + chunk < B ? lo + chunk : B, n = hi - lo;
+        cudaStream_t ps = env->pipe[k];
         if (obs_host && (st = cudaMemcpyAsync(obs_host + lo * N * D, b.obs + lo * N * D, sizeof(float) * n * N * D, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
             return cuda_fail(env, st, "D2H obs");
         if (reward_host && (st = cudaMemcpyAsync(reward_host + lo * N, b.reward + lo * N, sizeof(float) * n * N, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
@@ -265,10 +274,8 @@ extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *o
             return cuda_fail(env, st, "D2H done");
         if (message_host && (st = cudaMemcpyAsync(message_host + lo, b.message + lo, (size_t)n, cudaMemcpyDeviceToHost, ps)) != cudaSuccess)
             return cuda_fail(env, st, "D2H message");
-    }
-    for (int q = 0; q < 2; q++) {
-        if ((st = cudaEventRecord(env->ev_out[q], env->pipe[q])) != cudaSuccess) return cuda_fail(env, st, "cudaEventRecord");
-        if ((st = cudaStreamWaitEvent(s, env->ev_out[q], 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
+        if ((st = cudaEventRecord(env->ev_out[k], ps)) != cudaSuccess) return cuda_fail(env, st, "cudaEventRecord");
+        if ((st = cudaStreamWaitEvent(s, env->ev_out[k], 0)) != cudaSuccess) return cuda_fail(env, st, "cudaStreamWaitEvent");
     }
     if ((st = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(env, st, "mrb_step_host sync");
     return MRB_OK;

@@ -12,35 +12,6 @@
 
 namespace mrb {
 
-// 1/x without the IEEE fix-up path: MUFU seed + two Newton steps (relative error ~1e-16)
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-// one Newton step only: relative error ~2^-46 (1.4e-14).  Used where the value only scales a Newton
-// direction or a step length (the iteration recomputes its residuals, so this does not accumulate).
-__device__ __forceinline__ double fast_rcp1(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double hx = 0.5 * x;
-    r = r * fma(-hx * r, r, 1.5);
-    r = r * fma(-hx * r, r, 1.5);
-    return r;
-}
-
 template <int N>
 struct QpDual {
     static constexpr int n = 2 * N;

@@ -49,6 +49,13 @@ __device__ __forceinline__ double agent_step_size(const mrb_config &c, int i, in
     return c.step_dist;
 }
 
+// utilities/misc.py:23 np.linalg.norm(poses[:2,x]-poses[:2,agent]): the K-nearest order is decided on the
+// ROUNDED norm (near-ties on the spawn grid are common), so no FMA contraction and a real sqrt here
+__device__ __forceinline__ double neighbor_dist(double dx, double dy)
+{
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
 // ArcticTransport.py:136-143 get_cell_from_pose (int() truncates toward zero)
 __device__ __forceinline__ void arctic_cell(double x, double y, int &row, int &col)
 {
@@ -348,7 +355,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                     int best = -1; double bdist = 0.0;
 #pragma unroll
                     for (int b = 0; b < N; b++) {
-                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = dx * dx + dy * dy;
+                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = neighbor_dist(dx, dy);
                         if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
                     }
                     used |= 1u << best;
@@ -386,7 +393,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                     int best = -1; double bdist = 0.0;
 #pragma unroll
                     for (int b = 0; b < N; b++) {
-                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = dx * dx + dy * dy;
+                        const double dx = px[b] - px[a], dy = py[b] - py[a], dd = neighbor_dist(dx, dy);
                         if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
                     }
                     used |= 1u << best;

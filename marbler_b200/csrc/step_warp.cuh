@@ -9,6 +9,9 @@
 namespace mrb {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef MRB_WARP_MIN_BLOCKS
+#define MRB_WARP_MIN_BLOCKS 3      // <= 168 registers: 12 warps per SM (the 20-robot workspace is 14.7 KB per warp)
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -25,25 +28,29 @@ __device__ __forceinline__ double warp_max(double v)
 }
 __device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }   // a < b
 
-__host__ __device__ inline int qp_ld(int n) { return n | 1; }
+// Per-warp shared-memory workspace (doubles).  The Cholesky factor is stored as the lower triangle of
+// N x N blocks of 2 x 2 (block (i,k), k <= i, at 4 * (i (i + 1) / 2 + k): [xx, xy, yx, yy] = rows 2i, 2i+1 x
+// columns 2k, 2k+1), 32-byte aligned so that a block is two 128-bit shared loads.
 __host__ __device__ inline size_t warp_workspace_doubles(int N)
 {
-    const int n = 2 * N, m = N * (N - 1) / 2;
-    return (size_t)n * qp_ld(n) + 6 * (size_t)n + 5 * (size_t)(m > 0 ? m : 1);
+    const size_t n = 2 * (size_t)N, m = (size_t)N * (N - 1) / 2;
+    const size_t d = 2 * (size_t)N * (N + 1) + 6 * n + 4 * (m > 0 ? m : 1);
+    return (d + 1) & ~(size_t)1;
 }
 
 template <int PPL>
 struct QpWarp {
-    int N, n, m, ld, lane;
-    double *K, *invd, *vx, *vq, *vrx, *vdx, *xix, *xiy, *pax, *pay, *pw, *pz, *pt;
+    int N, n, m, lane;
+    double *Lb, *invd, *vx, *vq, *vrx, *vdx, *xix, *xiy, *pax, *pay, *pw, *pz, *pt;
     int pi[PPL], pj[PPL];
     bool pv[PPL];
     double ax[PPL], ay[PPL], h[PPL];
 
-    __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), ld(qp_ld(2 * N_)), lane(lane_)
+    __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), lane(lane_)
     {
-        K = ws; invd = K + (size_t)n * ld; vx = invd + n; vq = vx + n; vrx = vq + n; vdx = vrx + n;
-        xix = vdx + n; xiy = xix + N; pax = xiy + N; pay = pax + m; pw = pay + m; pz = pw + m; pt = pz + m;
+        Lb = ws; invd = Lb + 2 * (size_t)N * (N + 1); vx = invd + n; vq = vx + n; vrx = vq + n; vdx = vrx + n;
+        xix = vdx + n; xiy = xix + N; pax = xiy + N; pay = pax + m; pw = pay + m; pt = pw + m;
+        pz = pt;                                          // z and the right-hand-side multipliers are never live together
 #pragma unroll
         for (int k = 0; k < PPL; k++) {                   // decode my pair slots once
             const int c = lane + 32 * k;
@@ -53,6 +60,7 @@ struct QpWarp {
             pi[k] = i; pj[k] = i + 1 + rem;
         }
     }
+    __device__ __forceinline__ double *blk(int i, int k) const { return Lb + 4 * (size_t)(i * (i + 1) / 2 + k); }
 
     __device__ __forceinline__ void G_mul(const double *v, double (&out)[PPL]) const
     {
@@ -74,7 +82,8 @@ struct QpWarp {
             out[2 * lane] += sx; out[2 * lane + 1] += sy;
         }
     }
-    // K := 2I + G' diag(pw) G (lower triangle), then in-place Cholesky; invd = 1/diag(L)
+    // K := 2I + G' diag(pw) G, then in-place Cholesky by 2 x 2 blocks (left-looking; lane i owns block
+    // row i); invd = reciprocals of the diagonal of L
     __device__ void factor()
     {
         __syncwarp();
@@ -83,74 +92,91 @@ struct QpWarp {
             for (int j = 0; j < N; j++) {
                 if (j == lane) continue;
                 const int c = lane < j ? pair_index(lane, j, N) : pair_index(j, lane, N);
-                const double wx = pw[c] * pax[c], wy = pw[c] * pay[c];
-                dxx += wx * pax[c]; dxy += wx * pay[c]; dyy += wy * pay[c];
+                const double w = pw[c], a = pax[c], b = pay[c];
+                const double wa = w * a, wb = w * b;
+                const double pxx = wa * a, pxy = wa * b, pyy = wb * b;
+                dxx += pxx; dxy += pxy; dyy += pyy;
+                if (j < lane) {
+                    double2 *o = reinterpret_cast<double2 *>(blk(lane, j));
+                    o[0] = make_double2(-pxx, -pxy); o[1] = make_double2(-pxy, -pyy);
+                }
             }
-            K[(2 * lane) * ld + 2 * lane] = dxx;
-            K[(2 * lane + 1) * ld + 2 * lane] = dxy;
-            K[(2 * lane + 1) * ld + 2 * lane + 1] = dyy;
+            double2 *o = reinterpret_cast<double2 *>(blk(lane, lane));
+            o[0] = make_double2(dxx, 0.0); o[1] = make_double2(dxy, dyy);
         }
-#pragma unroll
-        for (int k = 0; k < PPL; k++)
-            if (pv[k]) {
-                const int c = lane + 32 * k, i = pi[k], j = pj[k];
-                const double wx = pw[c] * ax[k], wy = pw[c] * ay[k];
-                K[(2 * j) * ld + 2 * i] = -wx * ax[k]; K[(2 * j) * ld + 2 * i + 1] = -wx * ay[k];
-                K[(2 * j + 1) * ld + 2 * i] = -wx * ay[k]; K[(2 * j + 1) * ld + 2 * i + 1] = -wy * ay[k];
-            }
         __syncwarp();
-        for (int j = 0; j < n; j++) {                     // left-looking, one column per step
-            const int r0 = j + lane, r1 = j + lane + 32;
-            double a0 = 0.0, a1 = 0.0;
-            const double *Lj = K + (size_t)j * ld;
-            if (r0 < n) {
-                const double *Lr = K + (size_t)r0 * ld;
-                double acc = Lr[j], acc2 = 0.0;
-                int k = 0;
-                for (; k + 1 < j; k += 2) { acc -= Lr[k] * Lj[k]; acc2 -= Lr[k + 1] * Lj[k + 1]; }
-                if (k < j) acc -= Lr[k] * Lj[k];
-                a0 = acc + acc2;
+        const bool me = lane < N;
+        const double2 *ri = reinterpret_cast<const double2 *>(blk(me ? lane : 0, 0));
+        for (int j = 0; j < N; j++) {
+            // S = K_ij - sum_{k<j} L_ik L_jk'   (rows i >= j)
+            double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
+            if (me && lane >= j) {
+                const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
+                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
+                sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
+                double txx = 0.0, txy = 0.0, tyx = 0.0, tyy = 0.0;    // second set of accumulators: half the chain length
+                for (int k = 0; k < j; k++) {
+                    const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], j0 = rj[2 * k], j1 = rj[2 * k + 1];
+                    sxx = fma(-i0.x, j0.x, sxx); txx = fma(-i0.y, j0.y, txx);
+                    sxy = fma(-i0.x, j1.x, sxy); txy = fma(-i0.y, j1.y, txy);
+                    syx = fma(-i1.x, j0.x, syx); tyx = fma(-i1.y, j0.y, tyx);
+                    syy = fma(-i1.x, j1.x, syy); tyy = fma(-i1.y, j1.y, tyy);
+                }
+                sxx += txx; sxy += txy; syx += tyx; syy += tyy;
             }
-            if (r1 < n) {
-                const double *Lr = K + (size_t)r1 * ld;
-                double acc = Lr[j], acc2 = 0.0;
-                int k = 0;
-                for (; k + 1 < j; k += 2) { acc -= Lr[k] * Lj[k]; acc2 -= Lr[k + 1] * Lj[k + 1]; }
-                if (k < j) acc -= Lr[k] * Lj[k];
-                a1 = acc + acc2;
+            // diagonal block (lane j): L_jj = [l11 0; l21 l22]; every lane runs the arithmetic, lane j's is broadcast
+            double r1 = fast_rsqrt(sxx);
+            double l21 = syx * r1;
+            const double d2 = fma(-l21, l21, syy);
+            double r2 = fast_rsqrt(d2);
+            if (lane == j) {
+                double2 *o = reinterpret_cast<double2 *>(blk(j, j));
+                o[0] = make_double2(sxx * r1, 0.0); o[1] = make_double2(l21, d2 * r2);
+                invd[2 * j] = r1; invd[2 * j + 1] = r2;
             }
-            const double d = __shfl_sync(kFull, a0, 0);
-            double r = rsqrt(d);
-            r = r * (1.5 - 0.5 * d * r * r);
-            __syncwarp();
-            if (r0 < n) K[(size_t)r0 * ld + j] = a0 * r;
-            if (r1 < n) K[(size_t)r1 * ld + j] = a1 * r;
-            if (lane == 0) invd[j] = r;
+            r1 = __shfl_sync(kFull, r1, j); l21 = __shfl_sync(kFull, l21, j); r2 = __shfl_sync(kFull, r2, j);
+            if (me && lane > j) {                           // L_ij = S L_jj^-T
+                const double x00 = sxx * r1, x10 = syx * r1;
+                const double x01 = fma(-x00, l21, sxy) * r2, x11 = fma(-x10, l21, syy) * r2;
+                double2 *o = reinterpret_cast<double2 *>(blk(lane, j));
+                o[0] = make_double2(x00, x01); o[1] = make_double2(x10, x11);
+            }
             __syncwarp();
         }
     }
-    // b (smem) := K^-1 b
+    // b (smem) := K^-1 b, forward and backward substitution by blocks; lane i carries (b_2i, b_2i+1)
     __device__ void solve(double *b) const
     {
         __syncwarp();
-        double b0 = lane < n ? b[lane] : 0.0, b1 = lane + 32 < n ? b[lane + 32] : 0.0;
-        for (int k = 0; k < n; k++) {
-            const double bk = __shfl_sync(kFull, (k >> 5) ? b1 : b0, k & 31);
-            const double xk = bk * invd[k];
-            if (lane == (k & 31)) { if (k >> 5) b1 = xk; else b0 = xk; }
-            if (lane > k && lane < n) b0 -= K[(size_t)lane * ld + k] * xk;
-            if (lane + 32 > k && lane + 32 < n) b1 -= K[(size_t)(lane + 32) * ld + k] * xk;
+        const bool me = lane < N;
+        const int li = me ? lane : 0;
+        const double2 *ri = reinterpret_cast<const double2 *>(blk(li, 0));
+        double bx = me ? b[2 * li] : 0.0, by = me ? b[2 * li + 1] : 0.0;
+        const double r1 = invd[2 * li], r2 = invd[2 * li + 1], l21 = blk(li, li)[2];
+        for (int j = 0; j < N; j++) {
+            double y0 = bx * r1;
+            double y1 = fma(-l21, y0, by) * r2;
+            if (lane == j) { bx = y0; by = y1; }
+            y0 = __shfl_sync(kFull, y0, j); y1 = __shfl_sync(kFull, y1, j);
+            if (me && lane > j) {
+                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
+                bx = fma(-a0.x, y0, fma(-a0.y, y1, bx));
+                by = fma(-a1.x, y0, fma(-a1.y, y1, by));
+            }
         }
-        for (int k = n - 1; k >= 0; k--) {
-            const double bk = __shfl_sync(kFull, (k >> 5) ? b1 : b0, k & 31);
-            const double xk = bk * invd[k];
-            if (lane == (k & 31)) { if (k >> 5) b1 = xk; else b0 = xk; }
-            const double *Lk = K + (size_t)k * ld;
-            if (lane < k) b0 -= Lk[lane] * xk;
-            if (lane + 32 < k) b1 -= Lk[lane + 32] * xk;
+        for (int i = N - 1; i >= 0; i--) {
+            double x1 = by * r2;
+            double x0 = fma(-l21, x1, bx) * r1;
+            if (lane == i) { bx = x0; by = x1; }
+            x0 = __shfl_sync(kFull, x0, i); x1 = __shfl_sync(kFull, x1, i);
+            if (lane < i) {                                 // column `lane` of block row i: (L_i,lane)' x_i
+                const double2 *rw = reinterpret_cast<const double2 *>(blk(i, lane));
+                const double2 a0 = rw[0], a1 = rw[1];
+                bx = fma(-a0.x, x0, fma(-a1.x, x1, bx));
+                by = fma(-a0.y, x0, fma(-a1.y, x1, by));
+            }
         }
-        if (lane < n) b[lane] = b0;
-        if (lane + 32 < n) b[lane + 32] = b1;
+        if (me) { b[2 * lane] = bx; b[2 * lane + 1] = by; }
         __syncwarp();
     }
 
@@ -158,8 +184,8 @@ struct QpWarp {
     __device__ int run(double xi_x, double xi_y, double &ux, double &uy, bool barrier_default)
     {
         if (lane < N) {
-            const double nrm = sqrt(ux * ux + uy * uy);
-            if (nrm > kQpMagnitudeLimit) { const double sc = kQpMagnitudeLimit / nrm; ux *= sc; uy *= sc; }
+            const double n2 = ux * ux + uy * uy;
+            if (n2 > kQpMagnitudeLimit * kQpMagnitudeLimit) { const double sc = kQpMagnitudeLimit / sqrt(n2); ux *= sc; uy *= sc; }
         }
         if (m == 0) return 0;
         __syncwarp();
@@ -181,12 +207,13 @@ struct QpWarp {
                 ax[k] = 2.0 * ex; ay[k] = 2.0 * ey;
                 const int c = lane + 32 * k;
                 pax[c] = ax[k]; pay[c] = ay[k]; pw[c] = 1.0; pt[c] = h[k];
-                hh += h[k] * h[k];
+                hh = fma(h[k], h[k], hh);
             }
         }
         const double qq = warp_sum(lane < N ? 4.0 * (ux * ux + uy * uy) : 0.0);
         hh = warp_sum(hh);
-        const double resx0 = fmax(1.0, sqrt(qq)), resz0 = fmax(1.0, sqrt(hh));
+        // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2: cvxopt's residual tests without sqrt / division
+        const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
 
         // ---- default starting point
         factor();
@@ -202,10 +229,10 @@ struct QpWarp {
             if (pv[k]) {
                 z[k] -= h[k];
                 s[k] = -z[k];
-                ss += z[k] * z[k];
+                ss = fma(z[k], z[k], ss);
                 ts = fmax(ts, z[k]);
                 tz = fmax(tz, -z[k]);
-            } else { s[k] = 1.0; z[k] = 0.0; }
+            } else { s[k] = 1.0; z[k] = 1.0; }
         ss = warp_sum(ss); ts = warp_max(ts); tz = warp_max(tz);
         const double nrm = fmax(sqrt(ss), 1.0);
         double gap = 0.0;
@@ -214,7 +241,7 @@ struct QpWarp {
             if (pv[k]) {
                 if (ts >= -1e-8 * nrm) s[k] += 1.0 + ts;
                 if (tz >= -1e-8 * nrm) z[k] += 1.0 + tz;
-                gap += s[k] * z[k];
+                gap = fma(s[k], z[k], gap);
             }
         gap = warp_sum(gap);
 
@@ -222,14 +249,15 @@ struct QpWarp {
         for (; iters <= 50; iters++) {
             // rx = 2x + q + G'z ; rz = s + Gx - h
             double xq = 0.0, xrx = 0.0;
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < PPL; k++) if (pv[k]) pz[lane + 32 * k] = z[k];
             if (lane < N) {
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
-                    const double xv = vx[2 * lane + t], qv = vq[2 * lane + t], r = 2.0 * xv + qv;
+                    const double xv = vx[2 * lane + t], qv = vq[2 * lane + t], r = fma(2.0, xv, qv);
                     vrx[2 * lane + t] = r;
-                    xrx += xv * r; xq += xv * qv;
+                    xrx = fma(xv, r, xrx); xq = fma(xv, qv, xq);
                 }
             }
             __syncwarp();
@@ -242,27 +270,28 @@ struct QpWarp {
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     rz[k] += s[k] - h[k];
-                    resz += rz[k] * rz[k];
-                    zrz += z[k] * rz[k];
+                    resz = fma(rz[k], rz[k], resz);
+                    zrz = fma(z[k], rz[k], zrz);
                 }
             xq = warp_sum(xq); xrx = warp_sum(xrx); resx = warp_sum(resx); resz = warp_sum(resz); zrz = warp_sum(zrz);
             const double f0 = 0.5 * (xrx + xq);
             const double pcost = f0, dcost = f0 + zrz - gap;
             bool gap_ok = gap <= 1e-7;
-            if (pcost < 0.0) gap_ok = gap_ok || (gap / -pcost <= 1e-2);
-            else if (dcost > 0.0) gap_ok = gap_ok || (gap / dcost <= 1e-2);
-            const double pres = sqrt(resz) / resz0, dres = sqrt(resx) / resx0;
-            if ((pres <= 1e-2 && dres <= 1e-2 && gap_ok) || iters == 50) break;
+            if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
+            else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
+            if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
 
-            double w[PPL], sinv[PPL], t2[PPL], ds[PPL], dz[PPL];
+            double w[PPL], sinv[PPL], zinv[PPL], t2[PPL], ds[PPL], dz[PPL];
+            __syncwarp();                                   // every lane is done reading pz (= pt)
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    sinv[k] = 1.0 / s[k];
+                    sinv[k] = fast_rcp1(s[k]);
+                    zinv[k] = fast_rcp1(z[k]);
                     w[k] = z[k] * sinv[k];
                     pw[lane + 32 * k] = w[k];
                     pt[lane + 32 * k] = z[k] - w[k] * rz[k];
-                } else { sinv[k] = 1.0; w[k] = 0.0; }
+                } else { sinv[k] = 1.0; zinv[k] = 1.0; w[k] = 0.0; }
             factor();
             // predictor
             if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
@@ -278,11 +307,11 @@ struct QpWarp {
                     dz[k] = -z[k] - w[k] * ds[k];
                     t2[k] = ds[k] * dz[k];
                     dsdz += t2[k];
-                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] / z[k]));
+                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] * zinv[k]));
                 } else t2[k] = 0.0;
             dsdz = warp_sum(dsdz); tmax = warp_max(tmax);
-            double step = tmax == 0.0 ? 1.0 : fmin(1.0, 1.0 / tmax);
-            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz / gap * (step * step)));
+            double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);            // t == 0 ? 1 : min(1, 1/t)
+            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
             const double sigmamu = sg * sg * sg * (gap / m);
             // corrector
             __syncwarp();
@@ -303,18 +332,18 @@ struct QpWarp {
                 if (pv[k]) {
                     ds[k] = -rz[k] - ds[k];
                     dz[k] = t2[k] - z[k] - w[k] * ds[k];
-                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] / z[k]));
+                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] * zinv[k]));
                 }
             tmax = warp_max(tmax);
-            step = tmax == 0.0 ? 1.0 : fmin(1.0, 0.99 / tmax);
+            step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);           // t == 0 ? 1 : min(1, 0.99/t)
             if (lane < N) { vx[2 * lane] += step * vdx[2 * lane]; vx[2 * lane + 1] += step * vdx[2 * lane + 1]; }
             gap = 0.0;
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    s[k] += step * ds[k];
-                    z[k] += step * dz[k];
-                    gap += s[k] * z[k];
+                    s[k] = fma(step, ds[k], s[k]);
+                    z[k] = fma(step, dz[k], z[k]);
+                    gap = fma(s[k], z[k], gap);
                 }
             gap = warp_sum(gap);
             __syncwarp();
@@ -327,10 +356,10 @@ struct QpWarp {
 
 // ---- the step, lane = robot
 template <int SCN, int PPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MRB_WARP_MIN_BLOCKS)
 step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t env = p.env_lo + (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (env >= p.env_hi) return;
@@ -443,7 +472,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
             for (int kk = 0; kk < c.num_neighbors; kk++) {
                 int best = -1; double bdist = 0.0;
                 for (int b = 0; b < N; b++) {
-                    const double dx = spx[b] - px, dy = spy[b] - py, dd = dx * dx + dy * dy;
+                    const double dx = spx[b] - px, dy = spy[b] - py, dd = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
                     if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
                 }
                 used |= 1u << best;
@@ -643,11 +672,11 @@ inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cud
 
 // ---- barrier QP alone, one problem per warp
 template <int PPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MRB_WARP_MIN_BLOCKS)
 qp_warp_kernel(int N, int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
                double *__restrict__ u, int32_t *__restrict__ iters)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (e >= B) return;

@@ -103,7 +103,8 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
     st = env.get_state()
     ost = orc.unpack(sf, si)
     assert np.abs(st["poses"] - ost["poses"]).max() < 1e-12
-    n_done = n_msg = n_stalled = n_loose = 0
+    n_done = n_msg = n_stalled = n_loose = n_tie = 0
+    knn = scenario in ("PredatorCapturePrey", "Warehouse") and cfg.get("num_neighbors", 0) < orc.N - 1
     for t in range(T):
         a = rng.randint(0, orc.n_actions, size=(B, orc.N)).astype(np.int32)
         env.step(torch.as_tensor(a, device=env.device))
@@ -123,7 +124,19 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
         n_loose += int(loose.sum())
         assert perr[ok].max() < 1e-3, (t, perr[ok].max())
         tight = ok & ~loose
-        assert np.abs(env.obs.cpu().numpy() - obs)[tight].max() < POSE_TOL + F32_TOL, t
+        obs_ok = tight
+        if knn:
+            # K-nearest neighbour blocks (utilities/misc.py:20-25): on mirror-symmetric layouts (common on the
+            # spawn grid) two neighbours are EXACTLY equidistant and the order is decided by the last bit of
+            # the integrated poses (the reference's own argpartition order is unspecified there): skip the obs
+            # check for envs with such a tie, count them
+            P = ost["poses"]
+            d = np.hypot(P[:, 0, :, None] - P[:, 0, None, :], P[:, 1, :, None] - P[:, 1, None, :])
+            ds = np.sort(d, axis=2)
+            tie = (np.diff(ds[:, :, 1:], axis=2) < 1e-9).any(axis=(1, 2))
+            n_tie += int(tie.sum())
+            obs_ok = tight & ~tie
+        assert np.abs(env.obs.cpu().numpy() - obs)[obs_ok].max() < POSE_TOL + F32_TOL, t
         assert np.abs(env.reward.cpu().numpy() - rew)[tight].max() < POSE_TOL + F32_TOL, t
         assert np.abs(env.dist.cpu().numpy() - dist)[tight].max() < POSE_TOL + F32_TOL, t
         for k in gu.DISCRETE_STATE + ("episode_count",):
@@ -137,6 +150,7 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
     stats = env.read_stats()
     assert n_stalled <= max(2, int(stall_frac * B * T)), n_stalled
     assert n_loose <= max(2, int(1e-4 * B * T)), n_loose
+    assert n_tie <= max(4, int(5e-2 * B * T)), n_tie
     assert abs(stats["episodes"] - n_done) <= n_stalled and stats["env_steps"] == B * T
     assert stats["collisions"] + stats["boundary_exits"] >= n_msg - n_stalled
     assert stats["qp_stalls"] <= 4 * max(n_stalled, 1)
