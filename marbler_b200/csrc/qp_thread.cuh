@@ -74,7 +74,7 @@ struct QpThread {
             double d = L[tri(j, j)];
 #pragma unroll
             for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
-            const double r = fast_rsqrt(d);       // K >= 2I: always positive definite
+            const double r = fast_rsqrt(d);
             invd[j] = r;
 #pragma unroll
             for (int i = j + 1; i < n; i++) {
@@ -105,21 +105,15 @@ struct QpThread {
 
     // xi: SI points; u: in = nominal dxi (already norm-limited to 0.15 by the position controller),
     // out = certified velocities.  Returns the number of interior-point iterations.
-    //
-    // Code-size note: the factorisation and the triangular solves are ~n^3/3 fully unrolled instructions each.
-    // The default starting point (iters == -1), the predictor and the corrector therefore all go through ONE
-    // factor() and ONE solve() call site (a 1- or 2-trip `pass` loop that is deliberately not unrolled): the
-    // N = 6 kernel with three inlined copies did not fit the instruction cache (25 % of stall samples "no
-    // instruction", profiles/r01_ncu_step_thread_wh6_first.txt).
     __device__ __forceinline__ int run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N],
                                        double (&uy)[N], bool barrier_default)
     {
         double q[n], x[n];
 #pragma unroll
         for (int i = 0; i < N; i++) {          // A.8: pre-clip columns of dxi to norm 0.2, f = -2 dxi
-            const double n2 = ux[i] * ux[i] + uy[i] * uy[i];
-            if (n2 > kQpMagnitudeLimit * kQpMagnitudeLimit) {
-                const double sc = kQpMagnitudeLimit / sqrt(n2);
+            double nrm = sqrt(ux[i] * ux[i] + uy[i] * uy[i]);
+            if (nrm > kQpMagnitudeLimit) {
+                double sc = kQpMagnitudeLimit / nrm;
                 ux[i] *= sc; uy[i] *= sc;
             }
             q[2 * i] = -2.0 * ux[i];
@@ -135,141 +129,140 @@ struct QpThread {
             for (int i = 0; i < N - 1; i++)
 #pragma unroll
                 for (int j = i + 1; j < N; j++, c++) {
-                    const double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
-                    const double hv = (ex * ex + ey * ey) - r2;
-                    const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
+                    double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
+                    double hv = (ex * ex + ey * ey) - r2;
+                    double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
                     h[c] = gain * (hv * hv * hv);
                     ax[c] = 2.0 * ex; ay[c] = 2.0 * ey;
-                    hh = fma(h[c], h[c], hh);
+                    hh += h[c] * h[c];
                 }
 #pragma unroll
-            for (int a = 0; a < n; a++) qq = fma(q[a], q[a], qq);
+            for (int a = 0; a < n; a++) qq += q[a] * q[a];
         }
-        // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2: cvxopt's residual tests without sqrt / division
         const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
 
-        double s[m], z[m], w[m], sinv[m], zinv[m], t1[m], t2[m], rz[m], ds[m], dz[m];
-        double rx[n], dx[n];
+        double s[m], z[m], t1[m], t2[m];
+        // ---- default starting point: (2I + G'G) x = -q + G'h ; z = Gx - h ; s = -z ; shift
+#pragma unroll
+        for (int c = 0; c < m; c++) t1[c] = 1.0;
+        factor(t1);
+#pragma unroll
+        for (int a = 0; a < n; a++) x[a] = -q[a];
+        GT_acc(h, x);
+        solve(x);
+        G_mul(x, z);
+        double ss = 0.0, ts = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < m; c++) {
+            z[c] -= h[c];
+            s[c] = -z[c];
+            ss += z[c] * z[c];
+            ts = fmax(ts, z[c]);              // max(-s) = max(z)
+        }
+        const double nrm = fmax(sqrt(ss), 1.0);
+        double tz = -ts;                       // placeholder, recomputed below
+        tz = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < m; c++) tz = fmax(tz, -z[c]);
+        if (ts >= -1e-8 * nrm) {
+#pragma unroll
+            for (int c = 0; c < m; c++) s[c] += 1.0 + ts;
+        }
+        if (tz >= -1e-8 * nrm) {
+#pragma unroll
+            for (int c = 0; c < m; c++) z[c] += 1.0 + tz;
+        }
         double gap = 0.0;
 #pragma unroll
-        for (int c = 0; c < m; c++) { s[c] = 1.0; z[c] = 1.0; sinv[c] = 1.0; zinv[c] = 1.0; t2[c] = 0.0; rz[c] = 0.0; }
-#pragma unroll
-        for (int a = 0; a < n; a++) { x[a] = 0.0; rx[a] = 0.0; }
+        for (int c = 0; c < m; c++) gap += s[c] * z[c];
 
-        int iters = -1;                        // -1: the default starting point (A.9 step 2), then the iterations
-#pragma unroll 1
+        int iters = 0;
         for (; iters <= 50; iters++) {
-            const bool init = iters < 0;
-            if (!init) {
-                // rx = 2x + q + G'z ; f0 = 1/2 x'Px + q'x ; rz = s + Gx - h
-                double xq = 0.0, xrx = 0.0;
+            double rx[n], rz[m];
+            // rx = 2x + q + G'z ; f0 = 1/2 x'Px + q'x ; rz = s + Gx - h
+            double xq = 0.0, xrx = 0.0;
 #pragma unroll
-                for (int a = 0; a < n; a++) {
-                    rx[a] = fma(2.0, x[a], q[a]);
-                    xrx = fma(x[a], rx[a], xrx);
-                    xq = fma(x[a], q[a], xq);
-                }
-                const double f0 = 0.5 * (xrx + xq);
-                GT_acc(z, rx);
-                G_mul(x, rz);
-                double resx = 0.0, resz = 0.0, zrz = 0.0;
+            for (int a = 0; a < n; a++) {
+                rx[a] = 2.0 * x[a] + q[a];
+                xrx += x[a] * rx[a];
+                xq += x[a] * q[a];
+            }
+            const double f0 = 0.5 * (xrx + xq);
+            GT_acc(z, rx);
+            G_mul(x, rz);
+            double resx = 0.0, resz = 0.0, zrz = 0.0;
 #pragma unroll
-                for (int a = 0; a < n; a++) resx = fma(rx[a], rx[a], resx);
+            for (int a = 0; a < n; a++) resx += rx[a] * rx[a];
 #pragma unroll
-                for (int c = 0; c < m; c++) {
-                    rz[c] += s[c] - h[c];
-                    resz = fma(rz[c], rz[c], resz);
-                    zrz = fma(z[c], rz[c], zrz);
-                }
-                const double pcost = f0, dcost = f0 + zrz - gap;
-                // relgap <= reltol  <=>  gap <= 1e-2 * denominator;  pres <= feastol  <=>  resz <= (1e-2 resz0)^2
-                bool gap_ok = gap <= 1e-7;
-                if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
-                else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
-                if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
+            for (int c = 0; c < m; c++) {
+                rz[c] += s[c] - h[c];
+                resz += rz[c] * rz[c];
+                zrz += z[c] * rz[c];
+            }
+            const double pcost = f0, dcost = f0 + zrz - gap;
+            bool gap_ok = gap <= 1e-7;
+            if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
+            else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
+            if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
+
+            // w = z/s ; K = 2I + G' diag(w) G
+            double w[m], sinv[m], zinv[m];
 #pragma unroll
-                for (int c = 0; c < m; c++) {
-                    sinv[c] = fast_rcp1(s[c]);
-                    zinv[c] = fast_rcp1(z[c]);
-                    w[c] = z[c] * sinv[c];                     // K = 2I + G' diag(z/s) G
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < m; c++) w[c] = 1.0;        // (2I + G'G) x = -q + G'h
+            for (int c = 0; c < m; c++) {
+                sinv[c] = fast_rcp1(s[c]); zinv[c] = fast_rcp1(z[c]);
+                w[c] = z[c] * sinv[c];
             }
             factor(w);
 
-            double step = 1.0;
-#pragma unroll 1
-            for (int pass = init ? 0 : 1; pass < (init ? 1 : 3); pass++) {
-                // pass 0: starting point; pass 1: predictor (rc = -s.z); pass 2: corrector (rc = -s.z - ds.dz + sigma mu)
-                //   K dx = -rx - G'((rc + z.rz)/s) = -rx + G'(z - w.rz - t2),   t2 = (rc + s.z)/s
+            // predictor: rc = -s.z  ->  K dx = -rx - G'((rc + z.rz)/s) = -rx - G'(w.rz - z)
+            double dx[n], ds[m], dz[m];
 #pragma unroll
-                for (int c = 0; c < m; c++) t1[c] = init ? h[c] : z[c] - w[c] * rz[c] - (pass == 2 ? t2[c] : 0.0);
+            for (int c = 0; c < m; c++) t1[c] = z[c] - w[c] * rz[c];
 #pragma unroll
-                for (int a = 0; a < n; a++) dx[a] = init ? -q[a] : -rx[a];
-                GT_acc(t1, dx);
-                solve(dx);
-                G_mul(dx, ds);
-                if (init) {
-                    // z = Gx - h ; s = -z ; shift both into the cone
-                    double ss = 0.0, ts = -INFINITY, tz = -INFINITY;
+            for (int a = 0; a < n; a++) dx[a] = -rx[a];
+            GT_acc(t1, dx);
+            solve(dx);
+            G_mul(dx, ds);
+            double dsdz = 0.0, tmax = 0.0;
 #pragma unroll
-                    for (int a = 0; a < n; a++) x[a] = dx[a];
-#pragma unroll
-                    for (int c = 0; c < m; c++) {
-                        z[c] = ds[c] - h[c];
-                        s[c] = -z[c];
-                        ss = fma(z[c], z[c], ss);
-                        ts = fmax(ts, z[c]);                   // max(-s) = max(z)
-                        tz = fmax(tz, -z[c]);
-                    }
-                    const double nrm = fmax(sqrt(ss), 1.0);
-                    if (ts >= -1e-8 * nrm) {
-#pragma unroll
-                        for (int c = 0; c < m; c++) s[c] += 1.0 + ts;
-                    }
-                    if (tz >= -1e-8 * nrm) {
-#pragma unroll
-                        for (int c = 0; c < m; c++) z[c] += 1.0 + tz;
-                    }
-                    gap = 0.0;
-#pragma unroll
-                    for (int c = 0; c < m; c++) gap = fma(s[c], z[c], gap);
-                } else {
-                    double dsdz = 0.0, tmax = 0.0;
-#pragma unroll
-                    for (int c = 0; c < m; c++) {
-                        ds[c] = -rz[c] - ds[c];
-                        dz[c] = (pass == 2 ? t2[c] : 0.0) - z[c] - w[c] * ds[c];       // (rc - z.ds)/s
-                        tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
-                        if (pass == 1) {
-                            const double p = ds[c] * dz[c];    // Mehrotra correction term
-                            dsdz += p;
-                            t2[c] = p;
-                        }
-                    }
-                    if (pass == 1) {
-                        step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);                    // t == 0 ? 1 : min(1, 1/t)
-                        const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
-                        const double sigmamu = sg * sg * sg * (gap / m);
-#pragma unroll
-                        for (int c = 0; c < m; c++) t2[c] = (sigmamu - t2[c]) * sinv[c];
-                    } else {
-                        step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);            // t == 0 ? 1 : min(1, 0.99/t)
-                    }
-                }
+            for (int c = 0; c < m; c++) {
+                ds[c] = -rz[c] - ds[c];
+                dz[c] = -z[c] - w[c] * ds[c];
+                t2[c] = ds[c] * dz[c];                     // Mehrotra correction term
+                dsdz += t2[c];
+                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
             }
-            if (!init) {
+            double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);
+            double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
+            const double sigmamu = sg * sg * sg * (gap / m);
+
+            // corrector: rc = -s.z - ds_aff.dz_aff + sigma mu
 #pragma unroll
-                for (int a = 0; a < n; a++) x[a] = fma(step, dx[a], x[a]);
-                gap = 0.0;
+            for (int c = 0; c < m; c++) {
+                t2[c] = (sigmamu - t2[c]) * sinv[c];       // (rc + s.z)/s
+                t1[c] = z[c] - w[c] * rz[c] - t2[c];       // -(rc + z.rz)/s
+            }
 #pragma unroll
-                for (int c = 0; c < m; c++) {
-                    s[c] = fma(step, ds[c], s[c]);
-                    z[c] = fma(step, dz[c], z[c]);
-                    gap = fma(s[c], z[c], gap);
-                }
+            for (int a = 0; a < n; a++) dx[a] = -rx[a];
+            GT_acc(t1, dx);
+            solve(dx);
+            G_mul(dx, ds);
+            tmax = 0.0;
+#pragma unroll
+            for (int c = 0; c < m; c++) {
+                ds[c] = -rz[c] - ds[c];
+                dz[c] = t2[c] - z[c] - w[c] * ds[c];       // (rc - z.ds)/s
+                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
+            }
+            step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);
+#pragma unroll
+            for (int a = 0; a < n; a++) x[a] += step * dx[a];
+            gap = 0.0;
+#pragma unroll
+            for (int c = 0; c < m; c++) {
+                s[c] += step * ds[c];
+                z[c] += step * dz[c];
+                gap += s[c] * z[c];
             }
         }
 #pragma unroll

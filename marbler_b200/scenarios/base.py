@@ -11,6 +11,7 @@ import torch
 
 from .. import spaces
 from ..config import objectview, obs_space_dim
+from ..reference_rng import sample_reset
 from ..vec_env import VecEnv
 
 MESSAGES = ("", "collision", "boundary", "collision_boundary")      # roboEnv.py:85-90
@@ -48,7 +49,7 @@ class BatchedScenario(BaseEnv):
     obs_low, obs_high = -1.5, 3.0
 
     def __init__(self, args, num_envs=1, device=None, seed=None, env_id0=0, auto_reset=None,
-                 track_dist=True, collect_stats=True):
+                 track_dist=True, collect_stats=True, reset_rng=None):
         if isinstance(args, dict):
             args = objectview(dict(args))
         self.args = args
@@ -57,6 +58,19 @@ class BatchedScenario(BaseEnv):
             # visualisation / gif capture is not part of the batched step path
             cfg = dict(cfg, show_figure_frequency=-1, save_gif=False)
         self.num_envs = int(num_envs)
+        # reset sampler: "reference" = numpy's global legacy RNG + Python's random, call for call as the
+        # reference draws (seed-for-seed episodes, single env only); "philox" = the in-kernel counter-based
+        # stream (same distribution; batched, sharding-invariant)
+        if reset_rng is None:
+            reset_rng = "reference" if self.num_envs == 1 else "philox"
+        if reset_rng not in ("reference", "philox"):
+            raise ValueError("reset_rng must be 'reference' or 'philox'")
+        if reset_rng == "reference" and self.num_envs != 1:
+            raise ValueError("reset_rng='reference' reproduces the reference's single global RNG stream: num_envs must be 1")
+        self.reset_rng = reset_rng
+        self._cfg = dict(cfg)
+        if reset_rng == "reference" and seed is None and cfg.get("seed", -1) != -1:
+            np.random.seed(cfg["seed"])         # e.g. PredatorCapturePrey.py:27-28 (global side effect, as the reference)
         if seed is None:                        # the reference seeds numpy when seed != -1 (e.g. PredatorCapturePrey.py:27-28)
             seed = cfg.get("seed", -1)
             seed = int(np.random.SeedSequence().entropy & (2 ** 63 - 1)) if seed == -1 else int(seed)
@@ -88,11 +102,16 @@ class BatchedScenario(BaseEnv):
         return p[0].cpu().numpy() if self.num_envs == 1 else p
 
     def reset(self, mask=None, seed=None):
-        obs = self.vec.reset(mask=mask, seed=seed)
+        if self.reset_rng == "reference":
+            st = sample_reset(self.scenario, self._cfg)
+            self.vec.set_state({k: np.asarray(v)[None] for k, v in st.items()})
+            self.vec.obs.zero_()
+        else:
+            self.vec.reset(mask=mask, seed=seed)
         if self.num_envs == 1:                  # e.g. PredatorCapturePrey.py:136: an all-zero observation
             self.episode_steps = 0
             return [[0] * self.vec.D] * self.num_robots
-        return obs
+        return self.vec.obs
 
     def step(self, actions_):
         if self.num_envs == 1:

@@ -63,3 +63,24 @@ def compare_step(g, out, s1, pose_tol, obs_tol, rew_tol, dist_tol, skip=()):
     assert err["reward"] <= rew_tol, err
     assert err["dist"] <= dist_tol, err
     return err
+
+
+EPISODES = os.path.join(GOLDEN, "episodes")
+
+
+def episode_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(EPISODES, "*.npz")))
+
+
+class Episodes(object):
+    """Whole reference trajectories from a config seed (oracle/gen_episodes.py)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(EPISODES, name + ".npz"))
+        self.scenario = str(z["scenario"])
+        self.cfg = json.loads(str(z["cfg_json"]))
+        self.py_seed = int(z["py_seed"])
+        for k in ("actions", "obs", "reward", "done", "message", "dist", "qp_max_iters", "reset_after"):
+            setattr(self, k, z[k])
+        self.resets = {k[6:]: z[k] for k in z.files if k.startswith("reset.")}
+        self.T = len(self.actions)
