@@ -113,9 +113,9 @@ int mrb_reset(mrb_env *env, const uint8_t *mask, uint64_t seed, void *cuda_strea
  * actions: device i32 [B][N]. */
 int mrb_step(mrb_env *env, const int32_t *actions, void *cuda_stream);
 /* same step with HOST buffers (pinned for full speed; pageable works): H2D actions, step, D2H
- * obs/reward/done/message, then synchronises.  Batches of >= 16,384 envs are cut into chunks that
- * alternate over two library-internal streams (ordered after the caller's stream) so that the PCIe
- * copies of one chunk overlap the kernel of the next.  NULL host outputs are skipped. */
+ * obs/reward/done/message, then synchronises.  Batches of >= 16,384 envs are cut into up to 8 chunks,
+ * each on its own library-internal stream (ordered after the caller's stream), so that the PCIe copies
+ * of one chunk overlap the kernels of the others.  NULL host outputs are skipped. */
 int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                   uint8_t *done_host, uint8_t *message_host, void *cuda_stream);
 /* unit entry for the barrier-certificate QP alone (rps create_single_integrator_barrier_certificate{,2}
@@ -123,6 +123,40 @@ int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, fl
  * iters i32 [B] (may be NULL). */
 int mrb_barrier_qp(int device, int32_t num_robots, int32_t barrier_default, int64_t num_problems,
                    const double *dxi, const double *xi, double *u, int32_t *iters, void *cuda_stream);
+
+/* ---- on-device policy: the reference's evaluation loop utilities/misc.py:134-221
+ * (run_env) calls utilities/rnn_agent.py:5-29 RNNAgent / utilities/rnn_ns_agent.py:5-36 RNNNSAgent on the
+ * host once per env step: q, h = model(obs, h); actions = argmax(q).  mrb_policy_act does that for every
+ * agent of every env in one kernel: fc1 -> ReLU -> GRUCell (or Linear+ReLU when use_rnn == 0) -> fc2 ->
+ * greedy argmax, TF32 tensor-core MMA with FP32 accumulation, reading the env's obs buffer and writing
+ * the actions buffer mrb_step consumes (no host round trip). */
+typedef struct mrb_policy_desc {
+    int32_t struct_size;        /* sizeof(mrb_policy_desc): ABI check */
+    int32_t obs_dim;            /* D: width of one agent's row in the obs buffer */
+    int32_t input_dim;          /* fc1.in_features = D (+ n_agents when obs_agent_id, misc.py:161-162) */
+    int32_t hidden_dim;         /* 64 or 128 (model json "hidden_dim") */
+    int32_t n_actions;          /* <= 24 */
+    int32_t n_agents;
+    int32_t obs_agent_id;       /* append the one-hot agent id to the observation */
+    int32_t use_rnn;            /* 1: nn.GRUCell, 0: nn.Linear + ReLU (rnn_agent.py:11-14) */
+    int32_t non_shared;         /* 1: one weight set per agent (RNNNSAgent), 0: one shared set */
+    int32_t reserved0;
+} mrb_policy_desc;
+typedef struct mrb_policy mrb_policy;
+/* weights: HOST float32, (non_shared ? n_agents : 1) sets back to back, each set in state_dict order and
+ * torch layout ([out][in] row-major): fc1.weight, fc1.bias, then rnn.weight_ih [3H][H], rnn.weight_hh [3H][H],
+ * rnn.bias_ih, rnn.bias_hh (use_rnn) or rnn.weight [H][H], rnn.bias (otherwise), then fc2.weight, fc2.bias. */
+int mrb_policy_create(const mrb_policy_desc *desc, int device, const float *weights, int64_t num_weights,
+                      mrb_policy **out);
+int mrb_policy_destroy(mrb_policy *policy);
+const char *mrb_policy_last_error(const mrb_policy *policy);
+/* obs f32 [B][N][D], hidden f32 [B][N][H] (in/out), actions i32 [B][N] (out), q f32 [B][N][n_actions] (out,
+ * may be NULL), fresh u8 [B] (may be NULL): envs flagged != 0 start a new episode - their hidden state and
+ * observation are taken as zero (run_env re-zeroes hs and feeds reset()'s all-zero obs, misc.py:156,219).
+ * All device pointers; stream-ordered, no synchronisation. */
+int mrb_policy_act(mrb_policy *policy, int64_t num_envs, const float *obs, float *hidden, int32_t *actions,
+                   float *q, const uint8_t *fresh, void *cuda_stream);
+
 /* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
 int64_t mrb_launch_count(void);
 

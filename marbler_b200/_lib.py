@@ -11,7 +11,7 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "collisions", "boundary_ex
               "env_steps", "qp_solves", "qp_iterations", "timeouts", "qp_stalls")
 SYMBOLS = ("mrb_version", "mrb_create", "mrb_destroy", "mrb_last_error", "mrb_state_rows", "mrb_obs_dim",
            "mrb_num_actions", "mrb_bind", "mrb_reset", "mrb_step", "mrb_step_host", "mrb_barrier_qp",
-           "mrb_launch_count")
+           "mrb_launch_count", "mrb_policy_create", "mrb_policy_destroy", "mrb_policy_last_error", "mrb_policy_act")
 
 
 class Spawn(C.Structure):
@@ -38,6 +38,11 @@ class Config(C.Structure):
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state_f64", "state_i32", "obs", "reward", "done", "message",
                                           "remaining", "dist", "stats")]
+
+
+class PolicyDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("struct_size", "obs_dim", "input_dim", "hidden_dim", "n_actions", "n_agents",
+                                         "obs_agent_id", "use_rnn", "non_shared", "reserved0")]
 
 
 _lib = None
@@ -67,6 +72,10 @@ def load():
         "mrb_step_host": ([vp, vp, vp, vp, vp, vp, vp], C.c_int),
         "mrb_barrier_qp": ([C.c_int, i32, i32, i64, vp, vp, vp, vp, vp], C.c_int),
         "mrb_launch_count": ([], i64),
+        "mrb_policy_create": ([C.POINTER(PolicyDesc), C.c_int, vp, i64, C.POINTER(vp)], C.c_int),
+        "mrb_policy_destroy": ([vp], C.c_int),
+        "mrb_policy_last_error": ([vp], C.c_char_p),
+        "mrb_policy_act": ([vp, i64, vp, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         f = getattr(L, name)
@@ -75,6 +84,12 @@ def load():
         raise RuntimeError("marbler_b200: ABI version mismatch between _lib.py and %s" % LIB_PATH)
     _lib = L
     return L
+
+
+def check_policy(rc, handle=None):
+    if rc != 0:
+        msg = load().mrb_policy_last_error(handle)
+        raise RuntimeError("marbler_b200 policy error %d: %s" % (rc, (msg or b"").decode()))
 
 
 def check(rc, handle=None):

@@ -27,6 +27,7 @@ struct mrb_env {
 
 static std::string g_create_error;
 static std::atomic<int64_t> g_launches{0};
+namespace mrb { void count_launch() { g_launches++; } }
 
 static int fail(mrb_env *e, int code, const std::string &msg)
 {

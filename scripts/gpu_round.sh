@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/t.log 2>&1; grep -E "passed|failed" gpurun_out/t.log; grep -E "^E  |^FAILED" gpurun_out/t.log | head -20
-python bench.py --scenario Warehouse --envs 262144 --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench_wh.json 2> gpurun_out/bench_wh.err; cut -c1-200 gpurun_out/bench_wh.json
+(time timeout 600 python -m pytest tests/test_policy.py -m gpu -q) > gpurun_out/t.log 2>&1; grep -E "passed|failed" gpurun_out/t.log; grep -E "^E  |^FAILED|Error" gpurun_out/t.log | head -30 | cut -c1-300
+python scripts/policy_time.py 2>&1 | tail -5
