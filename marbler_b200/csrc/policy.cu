@@ -6,25 +6,30 @@
 // agent of every env and writes the int32 actions buffer that mrb_step consumes.
 //
 // Mapping: a warp owns 16 rows = one agent index in 16 consecutive envs (rows of one agent share a weight
-// set, so non-shared agents cost nothing extra).  All three layers are TF32 m16n8k8 tensor-core MMAs with
-// FP32 accumulation.  The activations never leave registers: fc1's accumulator fragments are turned into
-// the next layer's A fragments with 8 warp shuffles per 16x8 tile, the hidden state is loaded once as A
-// fragments, and fc2 is accumulated tile by tile as the GRU produces h'.  Weights are rounded to TF32 and
-// laid out in fragment order ONCE on the host (mrb_policy_create), so staging them is a linear cp.async copy
-// and every B fragment is a single conflict-free 64/128-bit shared load; the GRU weights (6 H^2 floats,
-// 393 KB for H = 128) stream through a double-buffered 2 x 24.6 KB window, one 8-unit column tile at a time.
+// set, so non-shared agents cost nothing extra).  All three layers are FP16 m16n8k16 tensor-core MMAs with
+// FP32 accumulation (FP16 keeps the same 11-bit significand as TF32 at twice the MMA rate and half the
+// shared-memory bytes per flop - the first, TF32 m16n8k8 version of this kernel was bound by B-fragment
+// shared-memory loads, profiles/r01_ncu_policy_tf32.txt).  The activations never leave registers: the
+// accumulator fragments of two adjacent 16x8 output tiles ARE the A fragment of the next layer's 16x16
+// k-tile (no shuffles), the hidden state is loaded once as A fragments, and fc2 is accumulated as the GRU
+// produces h'.  Weights are rounded to FP16 and laid out in fragment order ONCE on the host
+// (mrb_policy_create), so staging them is a linear cp.async copy and every B fragment pair is a single
+// conflict-free 128-bit shared load; the GRU weights (6 H^2 halves, 197 KB for H = 128) stream through a
+// double-buffered 2 x 12.3 KB window, one 8-unit column tile at a time.
 #include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mrb {
 
-constexpr int kPolicyWarps = 4;          // 64 envs of one agent per CTA
-constexpr int kMaxKS1 = 8;               // fc1 input width <= 64
+constexpr int kPolicyWarps = 4;          // 64 envs of one agent per CTA share every staged weight tile
+constexpr int kMaxKS1 = 4;               // fc1 input width <= 64 (k-steps of 16)
 constexpr int kMaxAT = 3;                // n_actions <= 24
 
 struct PolicyParams {
@@ -33,37 +38,21 @@ struct PolicyParams {
     int64_t B;
     int32_t obs_dim, input_dim, n_actions, n_agents, obs_agent_id, non_shared;
     int32_t KS1, AT;                     // fc1 k-steps, fc2 column tiles
-    int32_t szW1, szW2, head_floats;     // packed section sizes (floats)
+    int32_t szW1, szW2, head_floats;     // packed section sizes (32-bit words)
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x)
+// two floats -> one .f16x2 register (lower column in the lower half)
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
 {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
 }
-// D = A (16x8, row) * B (8x8, col) + D, TF32 inputs, FP32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], float b0, float b1)
+// D = A (16x16, row) * B (16x8, col) + D, FP16 inputs, FP32 accumulate
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-}
-// accumulator fragment of a 16x8 tile (rows g, g+8; columns 2t, 2t+1) -> A fragment of the same tile
-// (rows g, g+8; columns t, t+4): column c of row g lives in lane 4g + c/2, element c & 1
-__device__ __forceinline__ void c_to_a(const float (&c)[4], uint32_t (&a)[4], int lane)
-{
-    const unsigned full = 0xffffffffu;
-    const int t = lane & 3, lo = (lane & ~3) | (t >> 1), hi = lo + 2;
-    const float v00 = __shfl_sync(full, c[0], lo), v01 = __shfl_sync(full, c[1], lo);
-    const float v10 = __shfl_sync(full, c[2], lo), v11 = __shfl_sync(full, c[3], lo);
-    const float w00 = __shfl_sync(full, c[0], hi), w01 = __shfl_sync(full, c[1], hi);
-    const float w10 = __shfl_sync(full, c[2], hi), w11 = __shfl_sync(full, c[3], hi);
-    const bool odd = t & 1;
-    a[0] = to_tf32(odd ? v01 : v00);
-    a[1] = to_tf32(odd ? v11 : v10);
-    a[2] = to_tf32(odd ? w01 : w00);
-    a[3] = to_tf32(odd ? w11 : w10);
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void cp_async16(float *dst_smem, const float *src)
 {
@@ -74,16 +63,22 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// sigma(x) = 1 / (1 + e^-x) and tanh(x) = 2 sigma(2x) - 1 on the SFU (ex2.approx + rcp.approx, ~2 ulp each): far below
+// the TF32 rounding of the matmul operands, and no range-reduction branches in the per-tile epilogue
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(2.f, __frcp_rn(1.f + __expf(-2.f * x)), -1.f); }
 
+#ifndef MRB_POLICY_MIN_BLOCKS
+#define MRB_POLICY_MIN_BLOCKS 4      // 128 registers, 16 warps per SM: measured 0.327 ms vs 0.344 (3) and 0.427 (2) for 262,144 agents
+#endif
 template <int H, bool RNN>
-__global__ void __launch_bounds__(kPolicyWarps * 32, 2)
+__global__ void __launch_bounds__(kPolicyWarps * 32, MRB_POLICY_MIN_BLOCKS)
 policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t *__restrict__ actions,
                   float *__restrict__ q_out, const uint8_t *__restrict__ fresh)
 {
     extern __shared__ __align__(16) float sm[];
-    constexpr int NT = H / 8, KS = H / 8, G = RNN ? 6 : 1;
-    constexpr int CHUNK = G * KS * 64;                       // floats per 8-unit column tile of the recurrent layer
+    constexpr int NT = H / 8, KS = H / 16, G = RNN ? 6 : 1;  // 8-column output tiles, 16-wide k-steps
+    constexpr int CHUNK = G * KS * 64;                       // 32-bit words per column tile of the recurrent layer
     constexpr int NB = RNN ? 6 * H : H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int agent = blockIdx.y;
@@ -106,7 +101,8 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
     const float *oA = obs + rA * D, *oB = obs + rB * D;
     float *hA_ptr = hidden + rA * H, *hB_ptr = hidden + rB * H;
 
-    // ---- observation (+ one-hot agent id, misc.py:161-162) as A fragments
+    // ---- observation (+ one-hot agent id, misc.py:161-162) as A fragments: a0 = (row g, cols 2t, 2t+1),
+    //      a1 = (row g+8, same cols), a2 / a3 = the same rows, cols 2t+8, 2t+9 of the 16-wide k-step
     uint32_t oa[kMaxKS1][4];
     auto in_val = [&](const float *o, bool zero, int c) -> float {
         if (c < D) return zero ? 0.f : o[c];
@@ -115,10 +111,11 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
 #pragma unroll
     for (int s = 0; s < kMaxKS1; s++) {
         if (s < p.KS1) {
-            oa[s][0] = to_tf32(in_val(oA, zA, 8 * s + t));
-            oa[s][1] = to_tf32(in_val(oB, zB, 8 * s + t));
-            oa[s][2] = to_tf32(in_val(oA, zA, 8 * s + t + 4));
-            oa[s][3] = to_tf32(in_val(oB, zB, 8 * s + t + 4));
+            const int c = 16 * s + 2 * t;
+            oa[s][0] = pack_h2(in_val(oA, zA, c), in_val(oA, zA, c + 1));
+            oa[s][1] = pack_h2(in_val(oB, zB, c), in_val(oB, zB, c + 1));
+            oa[s][2] = pack_h2(in_val(oA, zA, c + 8), in_val(oA, zA, c + 9));
+            oa[s][3] = pack_h2(in_val(oB, zB, c + 8), in_val(oB, zB, c + 9));
         } else {
             oa[s][0] = oa[s][1] = oa[s][2] = oa[s][3] = 0u;
         }
@@ -126,12 +123,16 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
     // ---- hidden state as A fragments (GRU only)
     uint32_t ha[RNN ? KS : 1][4];
     if (RNN) {
+        const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int s = 0; s < KS; s++) {
-            ha[s][0] = to_tf32(zA ? 0.f : hA_ptr[8 * s + t]);
-            ha[s][1] = to_tf32(zB ? 0.f : hB_ptr[8 * s + t]);
-            ha[s][2] = to_tf32(zA ? 0.f : hA_ptr[8 * s + t + 4]);
-            ha[s][3] = to_tf32(zB ? 0.f : hB_ptr[8 * s + t + 4]);
+            const int c = 16 * s + 2 * t;
+            const float2 a0 = zA ? zero2 : *reinterpret_cast<const float2 *>(hA_ptr + c);
+            const float2 a1 = zB ? zero2 : *reinterpret_cast<const float2 *>(hB_ptr + c);
+            const float2 a2 = zA ? zero2 : *reinterpret_cast<const float2 *>(hA_ptr + c + 8);
+            const float2 a3 = zB ? zero2 : *reinterpret_cast<const float2 *>(hB_ptr + c + 8);
+            ha[s][0] = pack_h2(a0.x, a0.y); ha[s][1] = pack_h2(a1.x, a1.y);
+            ha[s][2] = pack_h2(a2.x, a2.y); ha[s][3] = pack_h2(a3.x, a3.y);
         }
     }
 
@@ -139,20 +140,24 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
     __syncthreads();
 
     // ---- x = relu(fc1(obs))                                 rnn_agent.py:22
+    // the accumulator fragments (rows g, g+8; cols 2t, 2t+1) of output tiles 2k and 2k+1 are exactly the A
+    // fragment (a0, a1 | a2, a3) of k-step k of the next layer
     uint32_t xa[KS][4];
+    {
+        const uint2 *w1 = reinterpret_cast<const uint2 *>(sW1) + lane;
 #pragma unroll
-    for (int j = 0; j < NT; j++) {
-        const float2 b = *reinterpret_cast<const float2 *>(sB1 + 8 * j + 2 * t);
-        float acc[4] = {b.x, b.y, b.x, b.y};
+        for (int j = 0; j < NT; j++) {
+            const float2 b = *reinterpret_cast<const float2 *>(sB1 + 8 * j + 2 * t);
+            float acc[4] = {b.x, b.y, b.x, b.y};
 #pragma unroll
-        for (int s = 0; s < kMaxKS1; s++)
-            if (s < p.KS1) {
-                const float2 w = reinterpret_cast<const float2 *>(sW1)[(j * p.KS1 + s) * 32 + lane];
-                mma_tf32(acc, oa[s], w.x, w.y);
-            }
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[i] = fmaxf(acc[i], 0.f);
-        c_to_a(acc, xa[j], lane);
+            for (int s = 0; s < kMaxKS1; s++)
+                if (s < p.KS1) {
+                    const uint2 w = w1[(j * p.KS1 + s) * 32];
+                    mma_f16(acc, oa[s], w.x, w.y);
+                }
+            xa[j >> 1][(j & 1) * 2] = pack_h2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+            xa[j >> 1][(j & 1) * 2 + 1] = pack_h2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+        }
     }
 
     // ---- recurrent layer, one 8-unit column tile at a time; fc2 accumulated on the fly
@@ -162,6 +167,7 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
         const float2 b = jt < p.AT ? *reinterpret_cast<const float2 *>(sB2 + 8 * jt + 2 * t) : make_float2(0.f, 0.f);
         qacc[jt][0] = b.x; qacc[jt][1] = b.y; qacc[jt][2] = b.x; qacc[jt][3] = b.y;
     }
+    uint32_t hp[4] = {0u, 0u, 0u, 0u};                       // h' of the current pair of column tiles, A layout
 #pragma unroll 1
     for (int j = 0; j < NT; j++) {
         if (j + 1 < NT) {
@@ -172,14 +178,18 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
         cp_commit();
         cp_wait<1>();                                        // tile j has landed (tile j + 1 may be in flight)
         __syncthreads();
-        const float *cb = sChunk + (j & 1) * CHUNK;
+        const uint4 *c4 = reinterpret_cast<const uint4 *>(sChunk + (j & 1) * CHUNK) + lane;
         const int c0 = 8 * j + 2 * t;
         float hn[4];
         if (RNN) {
             // torch.nn.GRUCell: r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r (W_hn h + b_hn)),
             // h' = (1 - z) n + z h; weight_ih / weight_hh rows are the (r, z, n) gates in that order
             const float *bi = sBias, *bh = sBias + 3 * H;
+            // old h of this tile in accumulator layout (issued before the MMAs so that the latency is hidden)
+            const float2 oldA = zA ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2 *>(hA_ptr + c0);
+            const float2 oldB = zB ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2 *>(hB_ptr + c0);
             float ar[4], az[4], ai[4], ah[4];
+            float ar2[4] = {0.f, 0.f, 0.f, 0.f}, az2[4] = {0.f, 0.f, 0.f, 0.f};     // separate chains for the h-side products
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int c = c0 + (i & 1);
@@ -188,51 +198,53 @@ policy_act_kernel(const PolicyParams p, const float *obs, float *hidden, int32_t
                 ai[i] = bi[2 * H + c];
                 ah[i] = bh[2 * H + c];
             }
-            const float4 *c4 = reinterpret_cast<const float4 *>(cb);
 #pragma unroll
             for (int sp = 0; sp < KS / 2; sp++) {
-                float4 w;
-                w = c4[(0 * (KS / 2) + sp) * 32 + lane]; mma_tf32(ar, xa[2 * sp], w.x, w.y); mma_tf32(ar, xa[2 * sp + 1], w.z, w.w);
-                w = c4[(1 * (KS / 2) + sp) * 32 + lane]; mma_tf32(az, xa[2 * sp], w.x, w.y); mma_tf32(az, xa[2 * sp + 1], w.z, w.w);
-                w = c4[(2 * (KS / 2) + sp) * 32 + lane]; mma_tf32(ai, xa[2 * sp], w.x, w.y); mma_tf32(ai, xa[2 * sp + 1], w.z, w.w);
-                w = c4[(3 * (KS / 2) + sp) * 32 + lane]; mma_tf32(ar, ha[2 * sp], w.x, w.y); mma_tf32(ar, ha[2 * sp + 1], w.z, w.w);
-                w = c4[(4 * (KS / 2) + sp) * 32 + lane]; mma_tf32(az, ha[2 * sp], w.x, w.y); mma_tf32(az, ha[2 * sp + 1], w.z, w.w);
-                w = c4[(5 * (KS / 2) + sp) * 32 + lane]; mma_tf32(ah, ha[2 * sp], w.x, w.y); mma_tf32(ah, ha[2 * sp + 1], w.z, w.w);
+                uint4 w;
+                w = c4[(0 * (KS / 2) + sp) * 32]; mma_f16(ar, xa[2 * sp], w.x, w.y); mma_f16(ar, xa[2 * sp + 1], w.z, w.w);
+                w = c4[(1 * (KS / 2) + sp) * 32]; mma_f16(az, xa[2 * sp], w.x, w.y); mma_f16(az, xa[2 * sp + 1], w.z, w.w);
+                w = c4[(2 * (KS / 2) + sp) * 32]; mma_f16(ai, xa[2 * sp], w.x, w.y); mma_f16(ai, xa[2 * sp + 1], w.z, w.w);
+                w = c4[(3 * (KS / 2) + sp) * 32]; mma_f16(ar2, ha[2 * sp], w.x, w.y); mma_f16(ar2, ha[2 * sp + 1], w.z, w.w);
+                w = c4[(4 * (KS / 2) + sp) * 32]; mma_f16(az2, ha[2 * sp], w.x, w.y); mma_f16(az2, ha[2 * sp + 1], w.z, w.w);
+                w = c4[(5 * (KS / 2) + sp) * 32]; mma_f16(ah, ha[2 * sp], w.x, w.y); mma_f16(ah, ha[2 * sp + 1], w.z, w.w);
             }
-            const float2 oldA = zA ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2 *>(hA_ptr + c0);
-            const float2 oldB = zB ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2 *>(hB_ptr + c0);
             const float old[4] = {oldA.x, oldA.y, oldB.x, oldB.y};
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float r = sigmoidf_(ar[i]), z = sigmoidf_(az[i]);
-                const float n = tanhf(ai[i] + r * ah[i]);
+                const float r = sigmoidf_(ar[i] + ar2[i]), z = sigmoidf_(az[i] + az2[i]);
+                const float n = tanhf_(ai[i] + r * ah[i]);
                 hn[i] = (1.f - z) * n + z * old[i];
             }
         } else {
             // h = relu(rnn(x)) with rnn = nn.Linear                rnn_agent.py:26-27
             const float2 b = *reinterpret_cast<const float2 *>(sBias + c0);
             hn[0] = b.x; hn[1] = b.y; hn[2] = b.x; hn[3] = b.y;
-            const float4 *c4 = reinterpret_cast<const float4 *>(cb);
 #pragma unroll
             for (int sp = 0; sp < KS / 2; sp++) {
-                const float4 w = c4[sp * 32 + lane];
-                mma_tf32(hn, xa[2 * sp], w.x, w.y);
-                mma_tf32(hn, xa[2 * sp + 1], w.z, w.w);
+                const uint4 w = c4[sp * 32];
+                mma_f16(hn, xa[2 * sp], w.x, w.y);
+                mma_f16(hn, xa[2 * sp + 1], w.z, w.w);
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) hn[i] = fmaxf(hn[i], 0.f);
         }
         if (vA) *reinterpret_cast<float2 *>(hA_ptr + c0) = make_float2(hn[0], hn[1]);
         if (vB) *reinterpret_cast<float2 *>(hB_ptr + c0) = make_float2(hn[2], hn[3]);
-        // q += h'[:, tile j] * fc2.weight[:, tile j]'             rnn_agent.py:28
-        uint32_t hp[4];
-        c_to_a(hn, hp, lane);
+        // q += h'[:, tiles j-1, j] * fc2.weight[:, those columns]'   (every second tile)        rnn_agent.py:28
+        if (!(j & 1)) {
+            hp[0] = pack_h2(hn[0], hn[1]);
+            hp[1] = pack_h2(hn[2], hn[3]);
+        } else {
+            hp[2] = pack_h2(hn[0], hn[1]);
+            hp[3] = pack_h2(hn[2], hn[3]);
+            const uint2 *w2 = reinterpret_cast<const uint2 *>(sW2) + lane;
 #pragma unroll
-        for (int jt = 0; jt < kMaxAT; jt++)
-            if (jt < p.AT) {
-                const float2 w = reinterpret_cast<const float2 *>(sW2)[(jt * KS + j) * 32 + lane];
-                mma_tf32(qacc[jt], hp, w.x, w.y);
-            }
+            for (int jt = 0; jt < kMaxAT; jt++)
+                if (jt < p.AT) {
+                    const uint2 w = w2[(jt * KS + (j >> 1)) * 32];
+                    mma_f16(qacc[jt], hp, w.x, w.y);
+                }
+        }
         __syncthreads();                                     // everyone is done with buffer j & 1
     }
 
@@ -289,24 +301,22 @@ static int pfail(mrb_policy *p, int code, const std::string &msg)
     return code;
 }
 
-// cvt.rna.tf32.f32 on the host: round to 10 explicit mantissa bits, ties away from zero
-static float tf32_round(float x)
+// B fragment of W' for 8-column tile j, 16-wide k-step s (W in torch layout [out][in]; rows >= rows_valid and
+// columns >= cols_valid read as zero): lane (g, t) holds b0 = {W[r][16s+2t], W[r][16s+2t+1]} and
+// b1 = {W[r][16s+2t+8], W[r][16s+2t+9]} with r = row0 + 8j + g, each pair rounded to FP16 and packed low | high
+static uint32_t h2bits(float lo, float hi)
 {
-    uint32_t u;
-    std::memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) != 0x7f800000u) { u += 0x1000u; u &= 0xffffe000u; }
-    std::memcpy(&x, &u, 4);
-    return x;
+    const uint32_t a = __half_as_ushort(__float2half_rn(lo)), b = __half_as_ushort(__float2half_rn(hi));
+    return a | (b << 16);
 }
-
-// B fragments of W' for column tile j, k-step s (W in torch layout [out][in]; rows >= rows_valid and columns >=
-// cols_valid read as zero): lane (g, t) holds b0 = W[row0 + 8j + g][8s + t], b1 = W[row0 + 8j + g][8s + t + 4]
 static void frag(const float *W, int ld, int row0, int rows_valid, int cols_valid, int j, int s, int lane, float &b0, float &b1)
 {
     const int g = lane >> 2, t = lane & 3, r = 8 * j + g;
-    const int k0 = 8 * s + t, k1 = k0 + 4;
-    b0 = (r < rows_valid && k0 < cols_valid) ? tf32_round(W[(size_t)(row0 + r) * ld + k0]) : 0.f;
-    b1 = (r < rows_valid && k1 < cols_valid) ? tf32_round(W[(size_t)(row0 + r) * ld + k1]) : 0.f;
+    auto at = [&](int k) { return (r < rows_valid && k < cols_valid) ? W[(size_t)(row0 + r) * ld + k] : 0.f; };
+    const int k0 = 16 * s + 2 * t;
+    const uint32_t u0 = h2bits(at(k0), at(k0 + 1)), u1 = h2bits(at(k0 + 8), at(k0 + 9));
+    std::memcpy(&b0, &u0, 4);
+    std::memcpy(&b1, &u1, 4);
 }
 
 extern "C" const char *mrb_policy_last_error(const mrb_policy *p) { return p ? p->err.c_str() : g_policy_create_error.c_str(); }
@@ -322,7 +332,7 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
     if (H != 64 && H != 128) return pfail(nullptr, MRB_E_UNSUPPORTED, "mrb_policy_create: hidden_dim must be 64 or 128");
     if (A < 1 || A > 8 * kMaxAT) return pfail(nullptr, MRB_E_UNSUPPORTED, "mrb_policy_create: n_actions must be in [1, 24]");
     if (N < 1 || N > MRB_MAX_ROBOTS) return pfail(nullptr, MRB_E_ARG, "mrb_policy_create: n_agents must be in [1, 32]");
-    if (Din < 1 || Din > 8 * kMaxKS1) return pfail(nullptr, MRB_E_UNSUPPORTED, "mrb_policy_create: input_dim must be in [1, 64]");
+    if (Din < 1 || Din > 16 * kMaxKS1) return pfail(nullptr, MRB_E_UNSUPPORTED, "mrb_policy_create: input_dim must be in [1, 64]");
     if (Din != d.obs_dim + (d.obs_agent_id ? N : 0))
         return pfail(nullptr, MRB_E_ARG, "mrb_policy_create: input_dim must equal obs_dim (+ n_agents with obs_agent_id): "
                                          "these weights were trained on a different observation layout");
@@ -338,7 +348,7 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
     if ((st = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return pfail(nullptr, MRB_E_CUDA, cudaGetErrorString(st));
     if (prop.major != 10) return pfail(nullptr, MRB_E_UNSUPPORTED, "mrb_policy_create: kernels are built for sm_100a (B200) only");
 
-    const int KS1 = (Din + 7) / 8, NT = H / 8, KS = H / 8, AT = (A + 7) / 8, G = d.use_rnn ? 6 : 1;
+    const int KS1 = (Din + 15) / 16, NT = H / 8, KS = H / 16, AT = (A + 7) / 8, G = d.use_rnn ? 6 : 1;
     const int szW1 = NT * KS1 * 64, szW2 = AT * KS * 64, NB = d.use_rnn ? 6 * H : H;
     const int head = szW1 + H + NB + szW2 + AT * 8;
     const int chunk = G * KS * 64;

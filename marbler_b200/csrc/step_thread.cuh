@@ -13,7 +13,10 @@
 
 namespace mrb {
 
-constexpr int kThreadsPerBlock = 64;
+#ifndef MRB_THREADS_PER_BLOCK
+#define MRB_THREADS_PER_BLOCK 64
+#endif
+constexpr int kThreadsPerBlock = MRB_THREADS_PER_BLOCK;
 #ifndef MRB_MIN_BLOCKS
 #define MRB_MIN_BLOCKS 4
 #endif

@@ -7,8 +7,8 @@ For a few of the reference's trained models (scenarios/<S>/models/*.th + *.json)
 state_dict, a short sequence of observations, and what utilities/rnn_agent.py RNNAgent / utilities/
 rnn_ns_agent.py RNNNSAgent (imported unmodified) return when driven as utilities/misc.py:155-170 run_env drives
 them: q values, greedy actions and the final hidden state, in float32 (`q`, `actions`, `h`).  `q_tf32` /
-`h_tf32` are the same network evaluated with every matmul operand rounded to TF32 (what the CUDA kernel's
-tensor-core MMAs see) - the exact target of the kernel's arithmetic; the float32 numbers are the parity bar.
+`h_tf32` are the same network evaluated with every matmul operand rounded to FP16 (what the CUDA kernel's
+tensor-core MMAs see; same 11-bit significand as TF32, which the first version used - hence the names) - the exact target of the kernel's arithmetic; the float32 numbers are the parity bar.
 """
 import json
 import os
@@ -31,12 +31,13 @@ MODELS = [  # scenario, weights, model json, actor class, n_agents, env obs dim,
 
 
 def tf32(x):
-    u = x.contiguous().view(torch.int32)
-    return ((u + 0x1000) & ~0x1fff).view(torch.float32)
+    """Operand rounding of the kernel's tensor-core MMAs: FP16, round to nearest even (the first version of
+    the kernel used TF32, hence the historical names q_tf32 / h_tf32 of the emulated outputs)."""
+    return x.half().float()
 
 
 def tf32_agent(sd, prefix, use_rnn, x, h):
-    """RNNAgent.forward (rnn_agent.py:21-29) with TF32-rounded matmul operands, FP32 accumulation."""
+    """RNNAgent.forward (rnn_agent.py:21-29) with FP16-rounded matmul operands, FP32 accumulation."""
     lin = lambda v, w, b: tf32(v) @ tf32(sd[prefix + w]).t() + sd[prefix + b]
     x = torch.relu(lin(x, "fc1.weight", "fc1.bias"))
     if use_rnn:
