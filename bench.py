@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--override", action="append", default=[], help="config key=value (python literal)")
+    ap.add_argument("--rollout", action="store_true",
+                    help="also time the closed loop policy kernel -> step kernel (SURVEY 8f-1), random-init GRU agent")
     return ap.parse_args()
 
 
@@ -180,6 +182,42 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def time_rollout(env, steps):
+    """Closed loop on the device: policy kernel (fc1 -> GRUCell -> fc2 -> argmax, the reference's RNNAgent with
+    hidden_dim 128 and obs_agent_id, random-init weights) -> step kernel, replayed from a CUDA graph."""
+    import torch
+    from marbler_b200.policy import Policy, Rollout
+    g = torch.Generator().manual_seed(0)
+    H, Din, A = 128, env.D + env.N, env.n_actions
+    u = lambda *shape: (torch.rand(shape, generator=g) * 2 - 1) / (shape[-1] ** 0.5)
+    sd = {"fc1.weight": u(H, Din), "fc1.bias": u(H), "rnn.weight_ih": u(3 * H, H), "rnn.weight_hh": u(3 * H, H),
+          "rnn.bias_ih": u(3 * H), "rnn.bias_hh": u(3 * H), "fc2.weight": u(A, H), "fc2.bias": u(A)}
+    pol = Policy(sd, env.N, env.D, obs_agent_id=True, device=env.device)
+    ro = Rollout(env, pol, use_graph=True, steps_per_graph=16)
+    ro.reset()
+    ro.run(33)
+    steps = max(16, steps // 16 * 16)
+    e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    torch.cuda.synchronize()
+    e0.record()
+    ro.run(steps)
+    e1.record()
+    for _ in range(20):
+        pol.act(env.obs, ro.hidden, actions=ro.actions, fresh=env.done)
+    e2.record()
+    for _ in range(20):
+        env.step(ro.actions)
+    e3.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = 2.0 * env.B * env.N * (H * Din + 6 * H * H + H * A)
+    pol_ms = e1.elapsed_time(e2) / 20
+    return {"env_steps_per_s": env.B / (ms * 1e-3), "ms_per_step": ms, "policy_kernel_ms": pol_ms,
+            "step_kernel_ms": e2.elapsed_time(e3) / 20, "policy_tflops": flops / (pol_ms * 1e-3) / 1e12,
+            "steps": steps, "kernels_per_step": 2, "launch": "CUDA graph replay, 16 env steps per graph",
+            "policy": "RNNAgent hidden 128, GRUCell, obs_agent_id, greedy; FP16 m16n8k16 MMA, FP32 accumulate; random-init weights"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -249,6 +287,7 @@ def run_ours(args):
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_rate = world * B * Ke / float(e2e_s.item())
 
+    rollout = time_rollout(env, min(K, 320)) if args.rollout else None
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -297,6 +336,8 @@ def run_ours(args):
                 "api": "VecEnv.step_host -> mrb_step_host (pinned host buffers, one sync per step)"},
         "gpu_launches": int(launches),
     }
+    if args.rollout:
+        out["rollout"] = rollout
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _, _, _ = cpu_port_rate(args, cfg, args.cpu_seconds)
     print(json.dumps(out))

@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_policy.py -m gpu -q) > gpurun_out/t.log 2>&1; grep -E "passed|failed" gpurun_out/t.log; grep -E "^E  |^FAILED|Error" gpurun_out/t.log | head -30 | cut -c1-300
-timeout 120 python scripts/policy_time.py 2>&1 | grep policy
+for v in _W5 _W6 _W8; do
+  MARBLER_B200_LIB=$PWD/marbler_b200/libmarbler_b200$v.so python bench.py --scenario Warehouse --envs 262144 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_wh$v.json 2>/dev/null; echo "V$v"; python -c "
+import json;d=json.load(open('gpurun_out/bench_wh$v.json'));print(d['ms_per_step'])"
+done
