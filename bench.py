@@ -224,6 +224,8 @@ def run_ours(args):
     from marbler_b200 import build, sharding
     from marbler_b200.vec_env import VecEnv
     build.build()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank, world, local = sharding.init_distributed()
     if world == 1 and args.gpus > 1:
         raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))

@@ -257,6 +257,27 @@ def test_host_path_equals_device_path():
     assert torch.equal(a_env.done.cpu(), done) and torch.equal(a_env.message.cpu(), msg)
 
 
+@pytest.mark.parametrize("B", [40000, 70001])
+def test_chunked_host_path_equals_device_path(B):
+    """Batches >= 32,768 envs take the multi-stream chunked path of mrb_step_host (ragged last chunk included):
+    same results as one device-path launch, step after step, with auto-reset on."""
+    g = gu.Golden("PredatorCapturePrey_rollout")
+    a_env = _vec(g.scenario, g.cfg, B, seed=9, auto_reset=True)
+    b_env = _vec(g.scenario, g.cfg, B, seed=9, auto_reset=True)
+    a_env.reset(), b_env.reset()
+    rng = np.random.RandomState(1)
+    for _ in range(3):
+        a = rng.randint(0, 5, size=(B, 4)).astype(np.int32)
+        a_env.step(torch.as_tensor(a, device="cuda:0"))
+        obs, rew, done, msg = b_env.step_host(a)
+        torch.cuda.synchronize()
+        assert torch.equal(a_env.obs.cpu(), obs) and torch.equal(a_env.reward.cpu(), rew)
+        assert torch.equal(a_env.done.cpu(), done) and torch.equal(a_env.message.cpu(), msg)
+    assert torch.equal(a_env.state_f64, b_env.state_f64) and torch.equal(a_env.state_i32, b_env.state_i32)
+    sa, sb = a_env.read_stats(), b_env.read_stats()
+    assert sa["env_steps"] == sb["env_steps"] == 3 * B and sa["episodes"] == sb["episodes"]
+
+
 def test_wrapper_single_env_keeps_reference_types():
     import marbler_b200
     for key, n, d, na in (("PredatorCapturePrey-v0", 4, 16, 5), ("Warehouse-v0", 6, 18, 5), ("MaterialTransport-v0", 4, 9, 20),
@@ -301,3 +322,41 @@ def test_full_size_properties():
     steps = env.state_i32[0]
     assert int(steps.max()) == 3 and int(steps.min()) >= 1
     assert bool((env.obs[:, :, 2:4] >= -5).all())
+
+
+FULL_SIZE = [("Warehouse", 262144, {}), ("MaterialTransport", 262144, {}), ("ArcticTransport", 262144, {}),
+             ("PredatorCapturePrey", 131072, dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))]
+
+
+@pytest.mark.parametrize("scenario,B,over", FULL_SIZE, ids=[s + "-" + str(b) for s, b, _ in FULL_SIZE])
+def test_full_size_properties_other_configs(scenario, B, over):
+    """BASELINE configs 3-5 at their full per-GPU sizes: size-independent properties of the env step -
+    run-to-run determinism (bit-exact state, obs, flags), |v| <= 0.2 m/s displacement bound, wrapped headings,
+    violation => done, step counters advance by one, observations finite and inside the declared Box."""
+    cfg = dict(gu.Golden(scenario + "_rollout").cfg)
+    cfg.update(over)
+    runs = []
+    for _ in range(2):
+        env = _vec(scenario, cfg, B, seed=77, auto_reset=False)
+        env.reset()
+        gen = torch.Generator(device="cuda:0").manual_seed(9)
+        p0 = env.agent_poses.clone()
+        for _t in range(2):
+            a = torch.randint(0, env.n_actions, (B, env.N), generator=gen, device="cuda:0", dtype=torch.int32)
+            env.step(a)
+        torch.cuda.synchronize()
+        runs.append((env.state_f64.clone(), env.state_i32.clone(), env.obs.clone(), env.message.clone(),
+                     env.done.clone(), env.reward.clone()))
+    for x, y in zip(*runs):
+        assert torch.equal(x, y)
+    p1 = env.agent_poses
+    uf = cfg["update_frequency"]
+    assert float((p1[:, :2] - p0[:, :2]).norm(dim=1).max()) <= 2 * uf * 0.033 * 0.2 + 1e-9
+    assert float(p1[:, 2].abs().max()) <= np.pi + 1e-12
+    msg, done = runs[0][3], runs[0][4]
+    assert bool(((msg != 0) <= (done != 0)).all())
+    assert bool((env.state_i32[0] == 2).all())
+    assert bool(torch.isfinite(env.obs).all()) and bool(torch.isfinite(env.reward).all())
+    assert float(env.obs.min()) >= -5.0 and float(env.obs.max()) <= 150.0
+    stats = env.read_stats()
+    assert stats["env_steps"] == 2 * B and stats["qp_solves"] > 0
