@@ -4,6 +4,8 @@
 // pair l + 32 k); the 2N x 2N KKT matrix and the small vectors live in a per-warp shared-memory
 // workspace.  Same algorithm, constants and reference citations as step_thread.cuh / qp_thread.cuh.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mrb {
@@ -355,7 +357,10 @@ struct QpWarp {
 };
 
 // ---- the step, lane = robot
-template <int SCN, int PPL>
+// NC: compile-time team size (0 = read it from the config).  With a literal N the pair-index arithmetic, the
+// per-robot loops and the block-Cholesky trip counts fold into constants; instantiated for the 20-robot stress
+// configuration (BASELINE config 5), every other size takes the generic path.
+template <int SCN, int PPL, int NC = 0>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MRB_WARP_MIN_BLOCKS)
 step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
@@ -364,7 +369,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     const int64_t env = p.env_lo + (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
-    const int N = c.num_robots;
+    const int N = NC ? NC : c.num_robots;
     const int64_t S = p.B;
     double *sf = p.buf.state_f64 + env;
     int32_t *si = p.buf.state_i32 + env;
@@ -647,14 +652,14 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
 
 inline int pairs_per_lane(int N) { return (N * (N - 1) / 2 + 31) / 32; }
 
-template <int SCN, int PPL>
+template <int SCN, int PPL, int NC = 0>
 inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions, cudaStream_t s)
 {
     const size_t smem = warp_workspace_doubles(p.cfg.num_robots) * sizeof(double) * kWarpsPerBlock;
-    cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
     const unsigned grid = (unsigned)((p.env_hi - p.env_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    step_warp_kernel<SCN, PPL><<<grid, kWarpsPerBlock * 32, smem, s>>>(p, actions);
+    step_warp_kernel<SCN, PPL, NC><<<grid, kWarpsPerBlock * 32, smem, s>>>(p, actions);
     return cudaSuccess;
 }
 
@@ -662,6 +667,7 @@ template <int SCN>
 inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cudaStream_t s)
 {
     const int ppl = pairs_per_lane(p.cfg.num_robots);
+    if (SCN == MRB_PCP && p.cfg.num_robots == 20 && !std::getenv("MRB_WARP_GENERIC")) return launch_step_warp_ppl<SCN, 6, 20>(p, actions, s);
     if (ppl <= 1) return launch_step_warp_ppl<SCN, 1>(p, actions, s);
     if (ppl <= 2) return launch_step_warp_ppl<SCN, 2>(p, actions, s);
     if (ppl <= 4) return launch_step_warp_ppl<SCN, 4>(p, actions, s);

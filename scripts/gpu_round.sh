@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 300 --warmup 5 > gpurun_out/bench_pcp_8gpu.json 2> gpurun_out/bench_pcp_8gpu.err; cut -c1-330 gpurun_out/bench_pcp_8gpu.json; tail -2 gpurun_out/bench_pcp_8gpu.err | cut -c1-200
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --impl reference --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_ref_8gpu.json 2> gpurun_out/bench_ref_8gpu.err; cut -c1-200 gpurun_out/bench_ref_8gpu.json
+P20="--override predator=10 --override capture=10 --override ROBOT_INIT_RIGHT_THRESH=0.1 --override num_neighbors=3"
+python bench.py --envs 131072 --steps 10 --warmup 3 --no-cpu-baseline $P20 > gpurun_out/bench_pcp20_nc.json 2>&1; python -c "
+import json;d=json.load(open('gpurun_out/bench_pcp20_nc.json'));print('NC20', d['ms_per_step'])"
+MRB_WARP_GENERIC=1 python bench.py --envs 131072 --steps 10 --warmup 3 --no-cpu-baseline $P20 > gpurun_out/bench_pcp20_gen.json 2>&1; python -c "
+import json;d=json.load(open('gpurun_out/bench_pcp20_gen.json'));print('generic', d['ms_per_step'])"
+(timeout 900 python -m pytest tests -m gpu -x -q -k "PCP20 or chunked or full_size") > gpurun_out/t.log 2>&1; grep -E "passed|failed" gpurun_out/t.log; grep -E "^E  |^FAILED" gpurun_out/t.log | head -10 | cut -c1-300
