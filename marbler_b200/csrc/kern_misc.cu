@@ -25,11 +25,11 @@ cudaError_t launch_reset(const Params &p, const uint8_t *mask, cudaStream_t s)
 }
 
 template <int N>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(ThreadShape<N>::kThreads)
 qp_thread_kernel(int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
                  double *__restrict__ u, int32_t *__restrict__ iters)
 {
-    const int64_t e = (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * ThreadShape<N>::kThreads + threadIdx.x;
     if (e >= B) return;
     double xix[N], xiy[N], ux[N], uy[N];
 #pragma unroll
@@ -37,23 +37,36 @@ qp_thread_kernel(int64_t B, int barrier_default, const double *__restrict__ dxi,
         xix[i] = xi[i * B + e]; xiy[i] = xi[(N + i) * B + e];
         ux[i] = dxi[i * B + e]; uy[i] = dxi[(N + i) * B + e];
     }
-    QpForTeam<N> qp;
-    const int it = qp.run(xix, xiy, ux, uy, barrier_default != 0);
+    const int it = qp_run<N>(xix, xiy, ux, uy, barrier_default != 0, QpStore<N>());
 #pragma unroll
     for (int i = 0; i < N; i++) { u[i * B + e] = ux[i]; u[(N + i) * B + e] = uy[i]; }
     if (iters) iters[e] = it;
 }
 
+template <int N>
+static cudaError_t launch_qp_thread(int64_t B, int barrier_default, const double *dxi, const double *xi,
+                                    double *u, int32_t *iters, cudaStream_t s)
+{
+    constexpr size_t smem = QpStore<N>::kBytes;
+    constexpr int tpb = ThreadShape<N>::kThreads;
+    const unsigned grid = (unsigned)((B + tpb - 1) / tpb);
+    if (smem > 48 * 1024) {
+        static cudaError_t attr = cudaFuncSetAttribute(qp_thread_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr != cudaSuccess) return attr;
+    }
+    qp_thread_kernel<N><<<grid, tpb, smem, s>>>(B, barrier_default, dxi, xi, u, iters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_barrier_qp(int N, int barrier_default, int64_t B, const double *dxi, const double *xi, double *u,
                               int32_t *iters, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock);
     switch (N) {
-    case 2: qp_thread_kernel<2><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 3: qp_thread_kernel<3><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 4: qp_thread_kernel<4><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 5: qp_thread_kernel<5><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
-    case 6: qp_thread_kernel<6><<<grid, kThreadsPerBlock, 0, s>>>(B, barrier_default, dxi, xi, u, iters); break;
+    case 2: return launch_qp_thread<2>(B, barrier_default, dxi, xi, u, iters, s);
+    case 3: return launch_qp_thread<3>(B, barrier_default, dxi, xi, u, iters, s);
+    case 4: return launch_qp_thread<4>(B, barrier_default, dxi, xi, u, iters, s);
+    case 5: return launch_qp_thread<5>(B, barrier_default, dxi, xi, u, iters, s);
+    case 6: return launch_qp_thread<6>(B, barrier_default, dxi, xi, u, iters, s);
     default: return launch_qp_warp(N, barrier_default, B, dxi, xi, u, iters, s);
     }
     return cudaGetLastError();

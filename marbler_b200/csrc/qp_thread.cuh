@@ -17,96 +17,232 @@
 
 namespace mrb {
 
-template <int N>
+// Storage of the factor.  The 2N x 2N Cholesky factor is kept as N x N blocks of 2 x 2 (one block per robot
+// pair, [e0 e1; e2 e3] = rows 2a, 2a+1 x columns 2b, 2b+1).  The diagonal blocks live in registers as
+// (1/l11, 1/l22, l21).  The strictly-lower blocks of the first RS block rows live in SHARED memory, two 128-bit
+// words per block, interleaved over the threads of the CTA (word w of thread t at Ls[w * TPB + t]: conflict-free);
+// block rows >= RS stay in registers.  With everything in registers (RS = 0) a 6-robot team needs ~350 live
+// doubles per env and the kernel spills ~1.9 KB per thread to local memory; the factor is the one large array
+// whose accesses are few enough per flop (each block is read once per triangular solve, and the block-row
+// factorisation below reads 20 blocks and writes 15) to sit behind the 128 B/clk shared-memory pipe.
+//
+// The per-constraint vectors of the iteration (m = N(N-1)/2 numbers each) follow the same rule: the ones in
+// kVecMask (bit order: VecId) live in shared memory, one double per (vector, constraint) interleaved over the
+// threads like the factor; the others are register arrays.
+enum VecId { V_H = 0, V_RZ, V_T2, V_SINV, V_ZINV, V_DS, V_DZ, V_S, V_Z, V_W, V_AX, V_AY, V_COUNT };
+
+template <int LEN, int TPB, bool SHARED>
+struct MVec;
+template <int LEN, int TPB>
+struct MVec<LEN, TPB, false> {
+    double r[LEN];
+    __device__ __forceinline__ MVec(double *, int) {}
+    __device__ __forceinline__ double get(int c) const { return r[c]; }
+    __device__ __forceinline__ void set(int c, double v) { r[c] = v; }
+};
+template <int LEN, int TPB>
+struct MVec<LEN, TPB, true> {
+    double *base;
+    __device__ __forceinline__ MVec(double *vs, int slot) : base(vs + (size_t)slot * LEN * TPB) {}
+    // volatile: without it the compiler merges the repeated loads of one iteration into a single early load and
+    // keeps the value live (then spills it to local memory) -- the opposite of what this store is for
+    __device__ __forceinline__ double get(int c) const { return reinterpret_cast<const volatile double *>(base)[c * TPB]; }
+    __device__ __forceinline__ void set(int c, double v) { reinterpret_cast<volatile double *>(base)[c * TPB] = v; }
+};
+__device__ __forceinline__ void lds_block(uint32_t addr, uint32_t stride, double (&o)[4])
+{
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[2]), "=d"(o[3]) : "r"(addr + stride));
+}
+__device__ __forceinline__ void sts_block(uint32_t addr, uint32_t stride, const double (&o)[4])
+{
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(o[0]), "d"(o[1]));
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + stride), "d"(o[2]), "d"(o[3]));
+}
+
+// MRB_QP_RECOMPUTE: 1 = 1/s and 1/z are recomputed where they are used (same function of the same input: identical
+// bits) and the corrector's (ds, dz) are recomputed in the update pass instead of being stored: two SFU seeds and
+// ~10 flops per constraint buy four fewer per-constraint vectors to keep on chip.
+#ifndef MRB_QP_RECOMPUTE
+#define MRB_QP_RECOMPUTE 1
+#endif
+#ifndef MRB_QP_RECOMPUTE_INV          // 0: keep 1/s and 1/z as stored vectors even when (ds, dz) are recomputed
+#define MRB_QP_RECOMPUTE_INV MRB_QP_RECOMPUTE
+#endif
+
+template <int N, int RS_, int TPB, unsigned VMASK = 0>
 struct QpThread {
     static constexpr int n = 2 * N;
     static constexpr int m = N * (N - 1) / 2;
-    static constexpr int KT = n * (n + 1) / 2;
-    __device__ static constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }   // r >= c
+    static constexpr int RS = RS_ > N ? N : RS_;
+    static constexpr int MM = m > 0 ? m : 1;
+    __device__ static constexpr int lowidx(int a, int b) { return a * (a - 1) / 2 + b; }        // a > b
+    static constexpr int kSmemBlocks = RS * (RS - 1) / 2;
+    static constexpr int kSmemWords = 2 * kSmemBlocks;            // double2 words per thread
+    static constexpr int kRegBlocks = m - kSmemBlocks;
+    __device__ static constexpr int pair(int i, int j) { return i * (2 * N - i - 1) / 2 + (j - i - 1); }   // i < j
 
-    double ax[m > 0 ? m : 1], ay[m > 0 ? m : 1], h[m > 0 ? m : 1];
-    double L[KT], invd[n];
+    __device__ static constexpr bool in_smem(int id) { return (VMASK >> id) & 1u; }
+    __device__ static constexpr int slot(int id) { int k = 0; for (int b = 0; b < id; b++) k += (VMASK >> b) & 1u; return k; }
+    static constexpr int kSmemVecs = slot(V_COUNT);
+    static constexpr int kVecDoubles = kSmemVecs * MM;          // doubles per thread in the vector store
+    template <int ID> using Vec = MVec<MM, TPB, in_smem(ID)>;
 
-    // out[c] = (G v)_c
-    __device__ __forceinline__ void G_mul(const double (&v)[n], double (&out)[m > 0 ? m : 1]) const
+    Vec<V_AX> ax;
+    Vec<V_AY> ay;
+    double Lr[kRegBlocks > 0 ? kRegBlocks : 1][4];
+    double invd[n], l21[N];
+    uint32_t Ls;                 // shared-window address of this thread's first factor word
+    double *Vs;
+
+    template <int A, int B>
+    __device__ __forceinline__ void load_blk(double (&o)[4]) const
+    {
+        if constexpr (A < RS) {
+            lds_block(Ls + (2 * lowidx(A, B)) * TPB * 16, TPB * 16, o);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) o[e] = Lr[lowidx(A, B) - kSmemBlocks][e];
+        }
+    }
+    template <int A, int B>
+    __device__ __forceinline__ void store_blk(const double (&o)[4])
+    {
+        if constexpr (A < RS) {
+            sts_block(Ls + (2 * lowidx(A, B)) * TPB * 16, TPB * 16, o);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) Lr[lowidx(A, B) - kSmemBlocks][e] = o[e];
+        }
+    }
+
+    __device__ __forceinline__ QpThread(double2 *Ls_, double *Vs_) : ax(Vs_, slot(V_AX)), ay(Vs_, slot(V_AY)), Ls((uint32_t)__cvta_generic_to_shared(Ls_)), Vs(Vs_) {}
+
+    // sink(c, (G v)_c) for every constraint c
+    template <typename F>
+    __device__ __forceinline__ void G_mul(const double (&v)[n], F &&sink) const
     {
         int c = 0;
 #pragma unroll
         for (int i = 0; i < N - 1; i++)
 #pragma unroll
             for (int j = i + 1; j < N; j++, c++)
-                out[c] = ax[c] * (v[2 * j] - v[2 * i]) + ay[c] * (v[2 * j + 1] - v[2 * i + 1]);
+                sink(c, ax.get(c) * (v[2 * j] - v[2 * i]) + ay.get(c) * (v[2 * j + 1] - v[2 * i + 1]));
     }
-    // out += G' y
-    __device__ __forceinline__ void GT_acc(const double (&y)[m > 0 ? m : 1], double (&out)[n]) const
+    // out += G' y,  y given as a function of the constraint index
+    template <typename F>
+    __device__ __forceinline__ void GT_acc(F &&y, double (&out)[n]) const
     {
         int c = 0;
 #pragma unroll
         for (int i = 0; i < N - 1; i++)
 #pragma unroll
             for (int j = i + 1; j < N; j++, c++) {
-                double tx = ax[c] * y[c], ty = ay[c] * y[c];
+                const double yc = y(c);
+                const double tx = ax.get(c) * yc, ty = ay.get(c) * yc;
                 out[2 * i] -= tx; out[2 * i + 1] -= ty;
                 out[2 * j] += tx; out[2 * j + 1] += ty;
             }
     }
-    // L := chol(2I + G' diag(w) G)   (lower, packed; invd = 1/diag)
-    __device__ __forceinline__ void factor(const double (&w)[m > 0 ? m : 1])
+    // L := chol(2I + G' diag(w) G), one block row at a time (bordering): block row a is built in registers
+    // from the rows above it, L_ab = (K_ab - sum_{c<b} L_ac L_bc') L_bb^-T, then the diagonal block from
+    // K_aa - sum_c L_ac L_ac'.  K is never stored: K_ab = -w_c a_c a_c' for the pair c = (b, a).
+    template <typename W>
+    __device__ __forceinline__ void factor(W &&w)
     {
+        double dxx[N], dxy[N], dyy[N];
 #pragma unroll
-        for (int k = 0; k < KT; k++) L[k] = 0.0;
+        for (int a = 0; a < N; a++) { dxx[a] = 2.0; dxy[a] = 0.0; dyy[a] = 2.0; }
+        {
+            int c = 0;
 #pragma unroll
-        for (int a = 0; a < n; a++) L[tri(a, a)] = 2.0;
-        int c = 0;
+            for (int i = 0; i < N - 1; i++)
 #pragma unroll
-        for (int i = 0; i < N - 1; i++)
+                for (int j = i + 1; j < N; j++, c++) {
+                    const double wc = w(c), ac = ax.get(c), bc = ay.get(c);
+                    const double wx = wc * ac, wy = wc * bc;
+                    const double pxx = wx * ac, pxy = wx * bc, pyy = wy * bc;
+                    dxx[i] += pxx; dxy[i] += pxy; dyy[i] += pyy;
+                    dxx[j] += pxx; dxy[j] += pxy; dyy[j] += pyy;
+                }
+        }
+        static_for<0, N>([&](auto A_) {
+            constexpr int a = decltype(A_)::value;
+            double R[a > 0 ? a : 1][4] = {};
+            static_for<0, a>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                constexpr int c = pair(b, a);
+                const double wc = w(c), ac = ax.get(c), bc = ay.get(c);
+                const double wx = wc * ac, wy = wc * bc;
+                double s0 = -wx * ac, s1 = -wx * bc, s2 = s1, s3 = -wy * bc;
+                static_for<0, b>([&](auto C_) {
+                    constexpr int cc = decltype(C_)::value;
+                    double T[4];
+                    load_blk<b, cc>(T);
+                    s0 = fma(-R[cc][0], T[0], s0); s0 = fma(-R[cc][1], T[1], s0);
+                    s1 = fma(-R[cc][0], T[2], s1); s1 = fma(-R[cc][1], T[3], s1);
+                    s2 = fma(-R[cc][2], T[0], s2); s2 = fma(-R[cc][3], T[1], s2);
+                    s3 = fma(-R[cc][2], T[2], s3); s3 = fma(-R[cc][3], T[3], s3);
+                });
+                const double r1 = invd[2 * b], r2 = invd[2 * b + 1], lo = l21[b];
+                R[b][0] = s0 * r1; R[b][2] = s2 * r1;
+                R[b][1] = fma(-R[b][0], lo, s1) * r2;
+                R[b][3] = fma(-R[b][2], lo, s3) * r2;
+            });
+            double d0 = dxx[a], d1 = dxy[a], d2 = dyy[a];
 #pragma unroll
-            for (int j = i + 1; j < N; j++, c++) {
-                double wx = w[c] * ax[c], wy = w[c] * ay[c];
-                double pxx = wx * ax[c], pxy = wx * ay[c], pyy = wy * ay[c];
-                L[tri(2 * i, 2 * i)] += pxx; L[tri(2 * i + 1, 2 * i)] += pxy; L[tri(2 * i + 1, 2 * i + 1)] += pyy;
-                L[tri(2 * j, 2 * j)] += pxx; L[tri(2 * j + 1, 2 * j)] += pxy; L[tri(2 * j + 1, 2 * j + 1)] += pyy;
-                L[tri(2 * j, 2 * i)] -= pxx; L[tri(2 * j, 2 * i + 1)] -= pxy;
-                L[tri(2 * j + 1, 2 * i)] -= pxy; L[tri(2 * j + 1, 2 * i + 1)] -= pyy;
+            for (int b = 0; b < a; b++) {
+                d0 = fma(-R[b][0], R[b][0], d0); d0 = fma(-R[b][1], R[b][1], d0);
+                d1 = fma(-R[b][2], R[b][0], d1); d1 = fma(-R[b][3], R[b][1], d1);
+                d2 = fma(-R[b][2], R[b][2], d2); d2 = fma(-R[b][3], R[b][3], d2);
             }
-        static_for<0, n>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            double d = L[tri(j, j)];
-#pragma unroll
-            for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
-            const double r = fast_rsqrt(d);
-            invd[j] = r;
-#pragma unroll
-            for (int i = j + 1; i < n; i++) {
-                double v = L[tri(i, j)];
-#pragma unroll
-                for (int k = 0; k < j; k++) v -= L[tri(i, k)] * L[tri(j, k)];
-                L[tri(i, j)] = v * r;
-            }
+            const double r1 = fast_rsqrt(d0);
+            const double lo = d1 * r1;
+            const double r2 = fast_rsqrt(fma(-lo, lo, d2));
+            invd[2 * a] = r1; invd[2 * a + 1] = r2; l21[a] = lo;
+            static_for<0, a>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                store_blk<a, b>(R[b]);
+            });
         });
     }
-    __device__ __forceinline__ void solve(double (&b)[n]) const
+    // v := K^-1 v: block forward substitution, then block backward substitution in row order (after x_a is
+    // known, every earlier block row receives -L_ab' x_a), so each stored block is read once per sweep
+    __device__ __forceinline__ void solve(double (&v)[n]) const
     {
-        static_for<0, n>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            double v = b[i];
-#pragma unroll
-            for (int k = 0; k < i; k++) v -= L[tri(i, k)] * b[k];
-            b[i] = v * invd[i];
+        static_for<0, N>([&](auto A_) {
+            constexpr int a = decltype(A_)::value;
+            double bx = v[2 * a], by = v[2 * a + 1];
+            static_for<0, a>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                double T[4];
+                load_blk<a, b>(T);
+                bx = fma(-T[0], v[2 * b], bx); bx = fma(-T[1], v[2 * b + 1], bx);
+                by = fma(-T[2], v[2 * b], by); by = fma(-T[3], v[2 * b + 1], by);
+            });
+            const double y0 = bx * invd[2 * a];
+            v[2 * a] = y0;
+            v[2 * a + 1] = fma(-l21[a], y0, by) * invd[2 * a + 1];
         });
-        static_for<0, n>([&](auto I) {
-            constexpr int i = n - 1 - decltype(I)::value;
-            double v = b[i];
-#pragma unroll
-            for (int k = i + 1; k < n; k++) v -= L[tri(k, i)] * b[k];
-            b[i] = v * invd[i];
+        static_for<0, N>([&](auto A_) {
+            constexpr int a = N - 1 - decltype(A_)::value;
+            const double x1 = v[2 * a + 1] * invd[2 * a + 1];
+            const double x0 = fma(-l21[a], x1, v[2 * a]) * invd[2 * a];
+            v[2 * a] = x0; v[2 * a + 1] = x1;
+            static_for<0, a>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                double T[4];
+                load_blk<a, b>(T);
+                v[2 * b] = fma(-T[0], x0, v[2 * b]); v[2 * b] = fma(-T[2], x1, v[2 * b]);
+                v[2 * b + 1] = fma(-T[1], x0, v[2 * b + 1]); v[2 * b + 1] = fma(-T[3], x1, v[2 * b + 1]);
+            });
         });
     }
 
     // xi: SI points; u: in = nominal dxi (already norm-limited to 0.15 by the position controller),
     // out = certified velocities.  Returns the number of interior-point iterations.
-    __device__ __forceinline__ int run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N],
-                                       double (&uy)[N], bool barrier_default)
+    __device__ __forceinline__ int run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N], double (&uy)[N],
+                                       bool barrier_default)
     {
         double q[n], x[n];
 #pragma unroll
@@ -121,6 +257,17 @@ struct QpThread {
         }
         if (m == 0) return 0;                  // single robot: u = dxi
 
+        Vec<V_H> h(Vs, slot(V_H));
+        Vec<V_S> s(Vs, slot(V_S));
+        Vec<V_Z> z(Vs, slot(V_Z));
+        Vec<V_RZ> rz(Vs, slot(V_RZ));
+        Vec<V_T2> t2(Vs, slot(V_T2));
+        Vec<V_W> w(Vs, slot(V_W));
+        Vec<V_SINV> sinv(Vs, slot(V_SINV));
+        Vec<V_ZINV> zinv(Vs, slot(V_ZINV));
+        Vec<V_DS> ds(Vs, slot(V_DS));
+        Vec<V_DZ> dz(Vs, slot(V_DZ));
+
         const double r2 = barrier_default ? 0.17 * 0.17 : 0.2 * 0.2;
         double hh = 0.0, qq = 0.0;
         {
@@ -132,53 +279,47 @@ struct QpThread {
                     double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
                     double hv = (ex * ex + ey * ey) - r2;
                     double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
-                    h[c] = gain * (hv * hv * hv);
-                    ax[c] = 2.0 * ex; ay[c] = 2.0 * ey;
-                    hh += h[c] * h[c];
+                    const double hc = gain * (hv * hv * hv);
+                    h.set(c, hc);
+                    ax.set(c, 2.0 * ex); ay.set(c, 2.0 * ey);
+                    hh += hc * hc;
                 }
 #pragma unroll
             for (int a = 0; a < n; a++) qq += q[a] * q[a];
         }
         const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
 
-        double s[m], z[m], t1[m], t2[m];
         // ---- default starting point: (2I + G'G) x = -q + G'h ; z = Gx - h ; s = -z ; shift
-#pragma unroll
-        for (int c = 0; c < m; c++) t1[c] = 1.0;
-        factor(t1);
+        factor([](int) { return 1.0; });
 #pragma unroll
         for (int a = 0; a < n; a++) x[a] = -q[a];
-        GT_acc(h, x);
+        GT_acc([&](int c) { return h.get(c); }, x);
         solve(x);
-        G_mul(x, z);
-        double ss = 0.0, ts = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < m; c++) {
-            z[c] -= h[c];
-            s[c] = -z[c];
-            ss += z[c] * z[c];
-            ts = fmax(ts, z[c]);              // max(-s) = max(z)
-        }
+        double ss = 0.0, ts = -INFINITY, tz = -INFINITY;
+        G_mul(x, [&](int c, double gx) {
+            const double zc = gx - h.get(c);
+            z.set(c, zc);
+            ss += zc * zc;
+            ts = fmax(ts, zc);                // max(-s) = max(z)
+            tz = fmax(tz, -zc);
+        });
         const double nrm = fmax(sqrt(ss), 1.0);
-        double tz = -ts;                       // placeholder, recomputed below
-        tz = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < m; c++) tz = fmax(tz, -z[c]);
-        if (ts >= -1e-8 * nrm) {
-#pragma unroll
-            for (int c = 0; c < m; c++) s[c] += 1.0 + ts;
-        }
-        if (tz >= -1e-8 * nrm) {
-#pragma unroll
-            for (int c = 0; c < m; c++) z[c] += 1.0 + tz;
-        }
+        const double s_shift = ts >= -1e-8 * nrm ? 1.0 + ts : 0.0, z_shift = tz >= -1e-8 * nrm ? 1.0 + tz : 0.0;
+        const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;
 #pragma unroll
-        for (int c = 0; c < m; c++) gap += s[c] * z[c];
+        for (int c = 0; c < m; c++) {
+            const double z0 = z.get(c);
+            double sc = -z0, zc = z0;
+            if (do_s) sc += s_shift;
+            if (do_z) zc += z_shift;
+            s.set(c, sc); z.set(c, zc);
+            gap += sc * zc;
+        }
 
         int iters = 0;
         for (; iters <= 50; iters++) {
-            double rx[n], rz[m];
+            double rx[n];
             // rx = 2x + q + G'z ; f0 = 1/2 x'Px + q'x ; rz = s + Gx - h
             double xq = 0.0, xrx = 0.0;
 #pragma unroll
@@ -188,17 +329,16 @@ struct QpThread {
                 xq += x[a] * q[a];
             }
             const double f0 = 0.5 * (xrx + xq);
-            GT_acc(z, rx);
-            G_mul(x, rz);
+            GT_acc([&](int c) { return z.get(c); }, rx);
             double resx = 0.0, resz = 0.0, zrz = 0.0;
 #pragma unroll
             for (int a = 0; a < n; a++) resx += rx[a] * rx[a];
-#pragma unroll
-            for (int c = 0; c < m; c++) {
-                rz[c] += s[c] - h[c];
-                resz += rz[c] * rz[c];
-                zrz += z[c] * rz[c];
-            }
+            G_mul(x, [&](int c, double gx) {
+                const double r = gx + (s.get(c) - h.get(c));
+                rz.set(c, r);
+                resz += r * r;
+                zrz += z.get(c) * r;
+            });
             const double pcost = f0, dcost = f0 + zrz - gap;
             bool gap_ok = gap <= 1e-7;
             if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
@@ -206,64 +346,75 @@ struct QpThread {
             if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
 
             // w = z/s ; K = 2I + G' diag(w) G
-            double w[m], sinv[m], zinv[m];
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                sinv[c] = fast_rcp1(s[c]); zinv[c] = fast_rcp1(z[c]);
-                w[c] = z[c] * sinv[c];
+                const double si = fast_rcp1(s.get(c)), zc = z.get(c);
+                if (!MRB_QP_RECOMPUTE_INV) { sinv.set(c, si); zinv.set(c, fast_rcp1(zc)); }
+                w.set(c, zc * si);
             }
-            factor(w);
+            auto inv_s = [&](int c) { return MRB_QP_RECOMPUTE_INV ? fast_rcp1(s.get(c)) : sinv.get(c); };
+            auto inv_z = [&](int c) { return MRB_QP_RECOMPUTE_INV ? fast_rcp1(z.get(c)) : zinv.get(c); };
+            factor([&](int c) { return w.get(c); });
 
-            // predictor: rc = -s.z  ->  K dx = -rx - G'((rc + z.rz)/s) = -rx - G'(w.rz - z)
-            double dx[n], ds[m], dz[m];
-#pragma unroll
-            for (int c = 0; c < m; c++) t1[c] = z[c] - w[c] * rz[c];
+            // predictor (rc = -s.z):                 K dx = -rx - G'(w.rz - z)
+            // corrector (rc = -s.z - ds_aff.dz_aff + sigma mu):  K dx = -rx - G'(w.rz - z + t2),  t2 = (rc + s.z)/s
+            // (running one body twice under a runtime `pass` flag to halve the code was measured 2.5x slower)
+            double dx[n];
+            double tmax = 0.0;
 #pragma unroll
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
-            GT_acc(t1, dx);
+            GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c); }, dx);
             solve(dx);
-            G_mul(dx, ds);
-            double dsdz = 0.0, tmax = 0.0;
-#pragma unroll
-            for (int c = 0; c < m; c++) {
-                ds[c] = -rz[c] - ds[c];
-                dz[c] = -z[c] - w[c] * ds[c];
-                t2[c] = ds[c] * dz[c];                     // Mehrotra correction term
-                dsdz += t2[c];
-                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
-            }
+            double dsdz = 0.0;
+            G_mul(dx, [&](int c, double gd) {
+                const double dsc = -rz.get(c) - gd;
+                const double dzc = -z.get(c) - w.get(c) * dsc;
+                const double pr = dsc * dzc;                 // Mehrotra correction term
+                t2.set(c, pr);
+                dsdz += pr;
+                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dzc * inv_z(c)));
+            });
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);
             double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
             const double sigmamu = sg * sg * sg * (gap / m);
-
-            // corrector: rc = -s.z - ds_aff.dz_aff + sigma mu
 #pragma unroll
-            for (int c = 0; c < m; c++) {
-                t2[c] = (sigmamu - t2[c]) * sinv[c];       // (rc + s.z)/s
-                t1[c] = z[c] - w[c] * rz[c] - t2[c];       // -(rc + z.rz)/s
-            }
+            for (int c = 0; c < m; c++) t2.set(c, (sigmamu - t2.get(c)) * inv_s(c));         // (rc + s.z)/s
 #pragma unroll
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
-            GT_acc(t1, dx);
+            GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c) - t2.get(c); }, dx);   // -(rc + z.rz)/s
             solve(dx);
-            G_mul(dx, ds);
             tmax = 0.0;
-#pragma unroll
-            for (int c = 0; c < m; c++) {
-                ds[c] = -rz[c] - ds[c];
-                dz[c] = t2[c] - z[c] - w[c] * ds[c];       // (rc - z.ds)/s
-                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
-            }
+            G_mul(dx, [&](int c, double gd) {
+                const double dsc = -rz.get(c) - gd;
+                const double dzc = fma(-w.get(c), dsc, t2.get(c) - z.get(c));                 // (rc - z.ds)/s
+                if (!MRB_QP_RECOMPUTE) { ds.set(c, dsc); dz.set(c, dzc); }
+                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dzc * inv_z(c)));
+            });
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);
+            gap = 0.0;
+            if (MRB_QP_RECOMPUTE) {
+                // the same expressions again; dx is laundered so that the compiler does not keep the first pass's
+                // 2m results live across the step-length reduction
+#pragma unroll
+                for (int a = 0; a < n; a++) asm volatile("" : "+d"(dx[a]));
+                G_mul(dx, [&](int c, double gd) {
+                    const double dsc = -rz.get(c) - gd;
+                    const double zc0 = z.get(c);
+                    const double dzc = fma(-w.get(c), dsc, t2.get(c) - zc0);
+                    const double sc = fma(step, dsc, s.get(c)), zc = fma(step, dzc, zc0);
+                    s.set(c, sc); z.set(c, zc);
+                    gap = fma(sc, zc, gap);
+                });
+            } else {
+#pragma unroll
+                for (int c = 0; c < m; c++) {
+                    const double sc = fma(step, ds.get(c), s.get(c)), zc = fma(step, dz.get(c), z.get(c));
+                    s.set(c, sc); z.set(c, zc);
+                    gap = fma(sc, zc, gap);
+                }
+            }
 #pragma unroll
             for (int a = 0; a < n; a++) x[a] += step * dx[a];
-            gap = 0.0;
-#pragma unroll
-            for (int c = 0; c < m; c++) {
-                s[c] += step * ds[c];
-                z[c] += step * dz[c];
-                gap += s[c] * z[c];
-            }
         }
 #pragma unroll
         for (int i = 0; i < N; i++) {

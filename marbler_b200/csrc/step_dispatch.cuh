@@ -9,8 +9,14 @@ namespace mrb {
 template <int SCN, int N>
 inline cudaError_t launch_thread(const Params &p, const int32_t *actions, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + kThreadsPerBlock - 1) / kThreadsPerBlock);
-    step_thread_kernel<SCN, N><<<grid, kThreadsPerBlock, 0, s>>>(p, actions);
+    constexpr int tpb = ThreadShape<N>::kThreads;
+    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + tpb - 1) / tpb);
+    constexpr size_t smem = QpStore<N>::kBytes;
+    if (smem > 48 * 1024) {
+        static cudaError_t attr = cudaFuncSetAttribute(step_thread_kernel<SCN, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr != cudaSuccess) return attr;
+    }
+    step_thread_kernel<SCN, N><<<grid, tpb, smem, s>>>(p, actions);
     return cudaGetLastError();
 }
 
@@ -19,7 +25,8 @@ template <int SCN>
 inline cudaError_t launch_step_generic(const Params &p, const int32_t *actions, cudaStream_t s, bool *launched)
 {
     *launched = true;
-    switch (p.cfg.num_robots) {
+    static const bool force_warp = std::getenv("MRB_FORCE_WARP") != nullptr;      // measurement aid
+    if (!force_warp) switch (p.cfg.num_robots) {
     case 2: if (SCN != MRB_MATERIAL) return launch_thread<SCN, (SCN != MRB_MATERIAL ? 2 : 4)>(p, actions, s); break;
     case 3: if (SCN != MRB_MATERIAL) return launch_thread<SCN, (SCN != MRB_MATERIAL ? 3 : 4)>(p, actions, s); break;
     case 4: return launch_thread<SCN, 4>(p, actions, s);

@@ -16,14 +16,70 @@ namespace mrb {
 #ifndef MRB_THREADS_PER_BLOCK
 #define MRB_THREADS_PER_BLOCK 64
 #endif
-constexpr int kThreadsPerBlock = MRB_THREADS_PER_BLOCK;
 #ifndef MRB_MIN_BLOCKS
 #define MRB_MIN_BLOCKS 4
+#endif
+// teams of 5 and 6 robots: the CTA shape is set by the shared-memory QP store (see below), not by registers
+#ifndef MRB_THREADS_PER_BLOCK_PRIMAL
+#define MRB_THREADS_PER_BLOCK_PRIMAL 64
+#endif
+#ifndef MRB_MIN_BLOCKS_PRIMAL
+#define MRB_MIN_BLOCKS_PRIMAL 4
+#endif
+template <int N>
+struct ThreadShape {
+    static constexpr bool kPrimal = !(N >= 2 && N <= 4);
+    static constexpr int kThreads = kPrimal ? MRB_THREADS_PER_BLOCK_PRIMAL : MRB_THREADS_PER_BLOCK;
+    static constexpr int kMinBlocks = kPrimal ? MRB_MIN_BLOCKS_PRIMAL : MRB_MIN_BLOCKS;
+};
+
+// Teams of 5 and 6 robots (primal QP, qp_thread.cuh): which parts of the per-env QP state live in shared memory
+// instead of registers -- the leading MRB_QP_SMEM_ROWS block rows of the factor and the per-constraint vectors in
+// MRB_QP_SMEM_VECS (bits: VecId).  Defaults from the measurements in DESIGN.md section 4.
+#ifndef MRB_QP_SMEM_ROWS
+#define MRB_QP_SMEM_ROWS 6
+#endif
+#ifndef MRB_QP_SMEM_VECS
+#define MRB_QP_SMEM_VECS 0x07      // h, rz, t2
 #endif
 
 // up to 4 robots the constraint-space (dual) Newton system is the smaller one (m <= 6 < 2N)
 template <int N>
-using QpForTeam = std::conditional_t<(N >= 2 && N <= 4), QpDual<N>, QpThread<N>>;
+using QpForTeam = std::conditional_t<(N >= 2 && N <= 4), QpDual<N>, QpThread<N, MRB_QP_SMEM_ROWS, ThreadShape<N>::kThreads, MRB_QP_SMEM_VECS>>;
+
+// per-CTA shared store of the primal QP: [factor words (double2) | vectors (double)], interleaved over threads
+template <int N>
+struct QpStore {
+    static constexpr bool kPrimal = !(N >= 2 && N <= 4);
+    __host__ __device__ static constexpr int words()
+    {
+        if constexpr (kPrimal) return QpForTeam<N>::kSmemWords + (QpForTeam<N>::kVecDoubles + 1) / 2;
+        else return 0;
+    }
+    static constexpr size_t kBytes = (size_t)words() * ThreadShape<N>::kThreads * sizeof(double2);
+    double2 *Ls;
+    double *Vs;
+    __device__ __forceinline__ QpStore() : Ls(nullptr), Vs(nullptr)
+    {
+        if constexpr (kPrimal && words() > 0) {
+            extern __shared__ double2 store[];           // words() * threads per CTA, sized by the launcher
+            Ls = store + threadIdx.x;
+            Vs = reinterpret_cast<double *>(store + QpForTeam<N>::kSmemWords * ThreadShape<N>::kThreads) + threadIdx.x;
+        }
+    }
+};
+template <int N>
+__device__ __forceinline__ int qp_run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N], double (&uy)[N],
+                                      bool barrier_default, const QpStore<N> &st)
+{
+    if constexpr (N >= 2 && N <= 4) {
+        QpForTeam<N> qp;
+        return qp.run(xix, xiy, ux, uy, barrier_default);
+    } else {
+        QpForTeam<N> qp(st.Ls, st.Vs);
+        return qp.run(xix, xiy, ux, uy, barrier_default);
+    }
+}
 
 // every scenario's Agent.generate_goal: PredatorCapturePrey/agent.py:48-76, warehouse.py:19-45,
 // MaterialTransport.py:19-46, ArcticTransport/agent.py:114-137, simple.py:32-60
@@ -170,10 +226,10 @@ __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *ma
 
 // ---- the step
 template <int SCN, int N>
-__global__ void __launch_bounds__(kThreadsPerBlock, MRB_MIN_BLOCKS)
+__global__ void __launch_bounds__(ThreadShape<N>::kThreads, ThreadShape<N>::kMinBlocks)
 step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
-    const int64_t env = p.env_lo + (int64_t)blockIdx.x * kThreadsPerBlock + threadIdx.x;
+    const int64_t env = p.env_lo + (int64_t)blockIdx.x * ThreadShape<N>::kThreads + threadIdx.x;
     if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
     const int64_t S = p.B;
@@ -181,6 +237,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     int32_t *si = p.buf.state_i32 + env;
     int32_t *sci = si + 3 * S;
     double *scf = sf + (5 * N + 1) * S;
+    const QpStore<N> qp_store;
 
     double px[N], py[N], th[N], qx[N], qy[N];
     int act[N];
@@ -247,8 +304,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                 }
                 ux[i] = dx; uy[i] = dy;
             }
-            QpForTeam<N> qp;
-            const int it = qp.run(xix, xiy, ux, uy, c.barrier_default != 0);   // controller.py:23
+            const int it = qp_run<N>(xix, xiy, ux, uy, c.barrier_default != 0, qp_store);   // controller.py:23
             n_it += it;
             n_stall += it >= 25;
             n_qp++;

@@ -10,9 +10,12 @@
 
 namespace mrb {
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef MRB_WARPS_PER_BLOCK
+#define MRB_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = MRB_WARPS_PER_BLOCK;
 #ifndef MRB_WARP_MIN_BLOCKS
-#define MRB_WARP_MIN_BLOCKS 2      // 255 registers, 8 warps per SM: measured 4 % faster than 168 registers / 12 warps (spills)
+#define MRB_WARP_MIN_BLOCKS 3      // 168 registers, 12 warps per SM (the per-constraint vectors that used to force 255 registers are recomputed or read back from the workspace)
 #endif
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -46,7 +49,7 @@ struct QpWarp {
     double *Lb, *invd, *vx, *vq, *vrx, *vdx, *xix, *xiy, *pax, *pay, *pw, *pz, *pt;
     int pi[PPL], pj[PPL];
     bool pv[PPL];
-    double ax[PPL], ay[PPL], h[PPL];
+    double h[PPL];
 
     __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), lane(lane_)
     {
@@ -64,11 +67,15 @@ struct QpWarp {
     }
     __device__ __forceinline__ double *blk(int i, int k) const { return Lb + 4 * (size_t)(i * (i + 1) / 2 + k); }
 
+    // (G v)_c for my pair slots; the pair directions a_c are read back from the workspace (keeping them in
+    // registers as well costs 2 PPL doubles per lane, which is what caps the kernel at 8 warps per SM)
     __device__ __forceinline__ void G_mul(const double *v, double (&out)[PPL]) const
     {
 #pragma unroll
-        for (int k = 0; k < PPL; k++)
-            out[k] = pv[k] ? ax[k] * (v[2 * pj[k]] - v[2 * pi[k]]) + ay[k] * (v[2 * pj[k] + 1] - v[2 * pi[k] + 1]) : 0.0;
+        for (int k = 0; k < PPL; k++) {
+            const int c = pv[k] ? lane + 32 * k : 0;
+            out[k] = pv[k] ? pax[c] * (v[2 * pj[k]] - v[2 * pi[k]]) + pay[c] * (v[2 * pj[k] + 1] - v[2 * pi[k] + 1]) : 0.0;
+        }
     }
     // out (smem, robot lanes) += G' y, y in smem indexed by pair
     __device__ __forceinline__ void GT_acc(const double *y, double *out) const
@@ -200,15 +207,14 @@ struct QpWarp {
         double hh = 0.0;
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
-            ax[k] = ay[k] = h[k] = 0.0;
+            h[k] = 0.0;
             if (pv[k]) {
                 const double ex = xix[pi[k]] - xix[pj[k]], ey = xiy[pi[k]] - xiy[pj[k]];
                 const double hv = (ex * ex + ey * ey) - r2;
                 const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
                 h[k] = gain * (hv * hv * hv);
-                ax[k] = 2.0 * ex; ay[k] = 2.0 * ey;
                 const int c = lane + 32 * k;
-                pax[c] = ax[k]; pay[c] = ay[k]; pw[c] = 1.0; pt[c] = h[k];
+                pax[c] = 2.0 * ex; pay[c] = 2.0 * ey; pw[c] = 1.0; pt[c] = h[k];
                 hh = fma(h[k], h[k], hh);
             }
         }
@@ -283,33 +289,34 @@ struct QpWarp {
             else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
             if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
 
-            double w[PPL], sinv[PPL], zinv[PPL], t2[PPL], ds[PPL], dz[PPL];
+            // 1/s and 1/z are recomputed where they are used (same function of the same input: identical bits),
+            // w = z/s is read back from the workspace and the corrector's (ds, dz) are recomputed in the update
+            // pass: 6 PPL fewer live doubles per lane than storing them
+            double t2[PPL], gv[PPL];
             __syncwarp();                                   // every lane is done reading pz (= pt)
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    sinv[k] = fast_rcp1(s[k]);
-                    zinv[k] = fast_rcp1(z[k]);
-                    w[k] = z[k] * sinv[k];
-                    pw[lane + 32 * k] = w[k];
-                    pt[lane + 32 * k] = z[k] - w[k] * rz[k];
-                } else { sinv[k] = 1.0; zinv[k] = 1.0; w[k] = 0.0; }
+                    const double w = z[k] * fast_rcp1(s[k]);
+                    pw[lane + 32 * k] = w;
+                    pt[lane + 32 * k] = z[k] - w * rz[k];
+                }
             factor();
             // predictor
             if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
             __syncwarp();
             GT_acc(pt, vdx);
             solve(vdx);
-            G_mul(vdx, ds);
+            G_mul(vdx, gv);
             double dsdz = 0.0, tmax = 0.0;
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    ds[k] = -rz[k] - ds[k];
-                    dz[k] = -z[k] - w[k] * ds[k];
-                    t2[k] = ds[k] * dz[k];
+                    const double ds = -rz[k] - gv[k];
+                    const double dz = -z[k] - pw[lane + 32 * k] * ds;
+                    t2[k] = ds * dz;
                     dsdz += t2[k];
-                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] * zinv[k]));
+                    tmax = fmax(tmax, fmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])));
                 } else t2[k] = 0.0;
             dsdz = warp_sum(dsdz); tmax = warp_max(tmax);
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);            // t == 0 ? 1 : min(1, 1/t)
@@ -320,21 +327,21 @@ struct QpWarp {
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    t2[k] = (sigmamu - t2[k]) * sinv[k];
-                    pt[lane + 32 * k] = z[k] - w[k] * rz[k] - t2[k];
+                    t2[k] = (sigmamu - t2[k]) * fast_rcp1(s[k]);
+                    pt[lane + 32 * k] = z[k] - pw[lane + 32 * k] * rz[k] - t2[k];
                 }
             if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
             __syncwarp();
             GT_acc(pt, vdx);
             solve(vdx);
-            G_mul(vdx, ds);
+            G_mul(vdx, gv);
             tmax = 0.0;
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    ds[k] = -rz[k] - ds[k];
-                    dz[k] = t2[k] - z[k] - w[k] * ds[k];
-                    tmax = fmax(tmax, fmax(-ds[k] * sinv[k], -dz[k] * zinv[k]));
+                    const double ds = -rz[k] - gv[k];
+                    const double dz = fma(-pw[lane + 32 * k], ds, t2[k] - z[k]);
+                    tmax = fmax(tmax, fmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])));
                 }
             tmax = warp_max(tmax);
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);           // t == 0 ? 1 : min(1, 0.99/t)
@@ -343,8 +350,10 @@ struct QpWarp {
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
-                    s[k] = fma(step, ds[k], s[k]);
-                    z[k] = fma(step, dz[k], z[k]);
+                    const double ds = -rz[k] - gv[k];
+                    const double dz = fma(-pw[lane + 32 * k], ds, t2[k] - z[k]);
+                    s[k] = fma(step, ds, s[k]);
+                    z[k] = fma(step, dz, z[k]);
                     gap = fma(s[k], z[k], gap);
                 }
             gap = warp_sum(gap);

@@ -1,4 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-P20="--override predator=10 --override capture=10 --override ROBOT_INIT_RIGHT_THRESH=0.1 --override num_neighbors=3"
-ncu --set full --import-source on --clock-control none -k regex:step_warp -c 1 -o gpurun_out/ncu_pcp20c python bench.py --envs 16384 --steps 1 --warmup 3 --no-cpu-baseline $P20 > gpurun_out/ncu_pcp20c.log 2>&1
+for v in "" _whL _whM _whO; do
+  echo "variant '$v'"
+  MARBLER_B200_LIB=$PWD/marbler_b200/libmarbler_b200$v.so python scripts/quick_time.py Warehouse 262144 30 2>&1 | tail -1
+done 2>&1 | tee gpurun_out/wh_variants3.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "barrier_qp or Warehouse or team_sizes" > gpurun_out/t_wh.log 2>&1; tail -3 gpurun_out/t_wh.log
