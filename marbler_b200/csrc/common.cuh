@@ -22,10 +22,19 @@ constexpr double kQpMagnitudeLimit = 0.2;
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 6.28318530717958647692;
 
+// Host mirrors of the step outputs (mrb_step_host): device-visible aliases of the caller's pinned buffers.  When
+// set, the step kernel stores obs / reward / done / message there as well, so the results cross PCIe as posted
+// writes while the kernel is still running instead of in copy-engine transfers queued behind it.
+struct HostOut {
+    float *obs, *reward;
+    uint8_t *done, *message;
+};
+
 // Everything a kernel needs, passed by value (__grid_constant__).
 struct Params {
     mrb_config cfg;
     mrb_buffers buf;
+    HostOut hout;       // all null outside the direct host path
     int64_t B;          // envs on this device (row stride of the state arrays)
     int64_t env_lo, env_hi;   // this launch processes envs [env_lo, env_hi)
     int64_t env_id0;    // global id of env 0 (RNG stream offset of this rank)

@@ -17,6 +17,7 @@
 // conflict-free 128-bit shared load; the GRU weights (6 H^2 halves, 197 KB for H = 128) stream through a
 // double-buffered 2 x 12.3 KB window, one 8-unit column tile at a time.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -25,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "policy_tc.cuh"
 
 namespace mrb {
 
@@ -290,6 +292,8 @@ struct mrb_policy {
     mrb_policy_desc d;
     int device;
     float *wpack;
+    uint8_t *tc_img;            // tcgen05 path (hidden 128, GRU): canonical FP16 images, NULL otherwise
+    mrb::tc::Params tcp;
     PolicyParams p;
     size_t smem_bytes;
     std::string err;
@@ -391,17 +395,60 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
                     }
             }
     }
+    // tcgen05 path: hidden 128 + GRUCell (every shared-weight checkpoint the reference ships)
+    std::vector<uint8_t> tcimg;
+    mrb::tc::Params tcp;
+    std::memset(&tcp, 0, sizeof(tcp));
+    const bool use_tc = H == 128 && d.use_rnn && Din <= mrb::tc::kMaxKp1 && A <= mrb::tc::kNpad2;
+    if (use_tc) {
+        const int Kp1 = (Din + 15) / 16 * 16;
+        const int w1b = Kp1 / 8 * (H / 8 * 128), w2b = H / 8 * (mrb::tc::kNpad2 / 8 * 128), bb = mrb::tc::kBiasFloats * 4;
+        const int headb = w1b + w2b + bb;
+        const int64_t setb = headb + 6LL * mrb::tc::kSlabBytes;
+        tcimg.assign((size_t)setb * sets, 0);
+        for (int sidx = 0; sidx < sets; sidx++) {
+            const float *w = weights + per_set * sidx;
+            const float *fc1w = w, *fc1b = fc1w + (size_t)H * Din, *wih = fc1b + H, *whh = wih + (size_t)3 * H * H;
+            const float *bih = whh + (size_t)3 * H * H, *bhh = bih + 3 * H, *fc2w = bhh + 3 * H, *fc2b = fc2w + (size_t)A * H;
+            uint8_t *o = tcimg.data() + (size_t)setb * sidx;
+            mrb::tc::pack_canonical(o, fc1w, Din, 0, H, Din, H, Kp1);
+            mrb::tc::pack_canonical(o + w1b, fc2w, H, 0, A, H, mrb::tc::kNpad2, H);
+            float *bo = reinterpret_cast<float *>(o + w1b + w2b);
+            std::memcpy(bo, fc1b, sizeof(float) * H);
+            std::memcpy(bo + H, bih, sizeof(float) * 3 * H);
+            std::memcpy(bo + 4 * H, bhh, sizeof(float) * 3 * H);
+            for (int a = 0; a < A; a++) bo[7 * H + a] = fc2b[a];
+            for (int sl = 0; sl < 6; sl++)
+                mrb::tc::pack_canonical(o + headb + (size_t)sl * mrb::tc::kSlabBytes, (sl & 1) ? whh : wih, H, (sl >> 1) * H, H, H, H, H);
+        }
+        tcp.set_bytes = setb; tcp.obs_dim = d.obs_dim; tcp.input_dim = Din; tcp.n_actions = A; tcp.n_agents = N;
+        tcp.obs_agent_id = d.obs_agent_id; tcp.non_shared = d.non_shared; tcp.Kp1 = Kp1;
+        tcp.w1_bytes = w1b; tcp.w2_bytes = w2b; tcp.head_bytes = headb;
+    }
     mrb_policy *pol = new (std::nothrow) mrb_policy();
     if (!pol) return pfail(nullptr, MRB_E_ARG, "mrb_policy_create: out of host memory");
     pol->d = d;
     pol->device = device;
     pol->wpack = nullptr;
+    pol->tc_img = nullptr;
+    pol->tcp = tcp;
     if ((st = cudaSetDevice(device)) != cudaSuccess || (st = cudaMalloc(&pol->wpack, img.size() * sizeof(float))) != cudaSuccess ||
         (st = cudaMemcpy(pol->wpack, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
         const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
         if (pol->wpack) cudaFree(pol->wpack);
         delete pol;
         return pfail(nullptr, MRB_E_CUDA, msg);
+    }
+    if (use_tc) {
+        if ((st = cudaMalloc(&pol->tc_img, tcimg.size())) != cudaSuccess ||
+            (st = cudaMemcpy(pol->tc_img, tcimg.data(), tcimg.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
+            if (pol->tc_img) cudaFree(pol->tc_img);
+            cudaFree(pol->wpack);
+            delete pol;
+            return pfail(nullptr, MRB_E_CUDA, msg);
+        }
+        pol->tcp.img = pol->tc_img;
     }
     PolicyParams &p = pol->p;
     p.wpack = pol->wpack; p.set_floats = set_floats; p.B = 0;
@@ -418,6 +465,7 @@ extern "C" int mrb_policy_destroy(mrb_policy *p)
     if (!p) return MRB_E_ARG;
     cudaSetDevice(p->device);
     if (p->wpack) cudaFree(p->wpack);
+    if (p->tc_img) cudaFree(p->tc_img);
     delete p;
     return MRB_OK;
 }
@@ -443,6 +491,18 @@ extern "C" int mrb_policy_act(mrb_policy *pol, int64_t num_envs, const float *ob
     PolicyParams p = pol->p;
     p.B = num_envs;
     cudaStream_t s = (cudaStream_t)stream;
+    static const bool tc_on = [] { const char *e = std::getenv("MRB_POLICY_TC"); return e && e[0] == '1'; }();
+    if (pol->tc_img && tc_on) {
+        mrb::tc::Params tp = pol->tcp;
+        tp.B = num_envs;
+        if ((st = cudaFuncSetAttribute(mrb::tc::policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mrb::tc::Smem::total)) != cudaSuccess)
+            return pfail(pol, MRB_E_CUDA, std::string("policy kernel attribute: ") + cudaGetErrorString(st));
+        const dim3 grid((unsigned)((num_envs + mrb::tc::kRows - 1) / mrb::tc::kRows), (unsigned)tp.n_agents);
+        mrb::tc::policy_act_tc_kernel<<<grid, mrb::tc::kThreads, mrb::tc::Smem::total, s>>>(tp, obs, hidden, actions, q, fresh);
+        if ((st = cudaGetLastError()) != cudaSuccess) return pfail(pol, MRB_E_CUDA, std::string("policy kernel launch: ") + cudaGetErrorString(st));
+        count_launch();
+        return MRB_OK;
+    }
     const bool rnn = pol->d.use_rnn != 0;
     if (pol->d.hidden_dim == 128) st = rnn ? launch_policy<128, true>(pol, p, obs, hidden, actions, q, fresh, s)
                                             : launch_policy<128, false>(pol, p, obs, hidden, actions, q, fresh, s);

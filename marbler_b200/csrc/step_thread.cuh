@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(ThreadShape<N>::kThreads, ThreadShape<N>::kMin
 step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
     const int64_t env = p.env_lo + (int64_t)blockIdx.x * ThreadShape<N>::kThreads + threadIdx.x;
+    const unsigned warp_envs = __ballot_sync(0xffffffffu, env < p.env_hi);      // lanes of this warp that own an env
     if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
     const int64_t S = p.B;
@@ -632,6 +633,34 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     p.buf.done[env] = done ? 1 : 0;
     p.buf.message[env] = (uint8_t)msg;
     p.buf.remaining[env] = remaining;
+    if (p.hout.obs || p.hout.reward || p.hout.done || p.hout.message) {
+        // host mirrors.  The observations of a warp's envs are one contiguous block of obs[B][N][D]: re-read it
+        // warp-wide so that every store instruction sends 512 contiguous bytes over PCIe
+        const unsigned act = warp_envs;      // not __activemask(): lanes that diverged above must reconverge here
+        __syncwarp(act);
+        if (p.hout.obs) {
+            const int lane = threadIdx.x & 31, first = __ffs(act) - 1;
+            const int64_t env0 = __shfl_sync(act, env, first);
+            const int64_t words = (int64_t)__popc(act) * N * D;          // floats; N * D * 4 bytes need not be 16-byte sized
+            const float *src = p.buf.obs + env0 * (int64_t)(N * D);
+            float *dst = p.hout.obs + env0 * (int64_t)(N * D);
+            const int rank = __popc(act & ((1u << lane) - 1));
+            const int nact = __popc(act);
+            if ((((env0 * N * D) | words) & 3) == 0) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int64_t k = rank; k < words / 4; k += nact) d4[k] = s4[k];
+            } else {
+                for (int64_t k = rank; k < words; k += nact) dst[k] = src[k];
+            }
+        }
+        if (p.hout.reward) {
+#pragma unroll
+            for (int i = 0; i < N; i++) p.hout.reward[env * N + i] = rew[i];
+        }
+        if (p.hout.done) p.hout.done[env] = done ? 1 : 0;
+        if (p.hout.message) p.hout.message[env] = (uint8_t)msg;
+    }
     const double ep_return = sf[(5 * N) * S] + (double)team;
     sf[(5 * N) * S] = ep_return;
 

@@ -627,6 +627,19 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         p.buf.reward[env * N + lane] = rew;
         if (p.buf.dist) p.buf.dist[env * N + lane] = (float)dist;
     }
+    if (p.hout.obs) {                       // host mirror of this env's observation block (see step_thread.cuh)
+        __syncwarp();
+        const int64_t base = env * (int64_t)(N * D);
+        const int words = N * D;
+        if (((base | words) & 3) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(p.buf.obs + base);
+            float4 *d4 = reinterpret_cast<float4 *>(p.hout.obs + base);
+            for (int k = lane; k < words / 4; k += 32) d4[k] = s4[k];
+        } else {
+            for (int k = lane; k < words; k += 32) p.hout.obs[base + k] = p.buf.obs[base + k];
+        }
+    }
+    if (me && p.hout.reward) p.hout.reward[env * N + lane] = rew;
     float team = me ? rew : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) team += __shfl_xor_sync(kFull, team, o);
@@ -635,6 +648,8 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         si[0] = steps; si[S] = 1;
         p.buf.done[env] = done ? 1 : 0;
         p.buf.message[env] = (uint8_t)msg;
+        if (p.hout.done) p.hout.done[env] = done ? 1 : 0;
+        if (p.hout.message) p.hout.message[env] = (uint8_t)msg;
         p.buf.remaining[env] = remaining;
         ep_return = sf[(5 * N) * S] + (double)team;
         sf[(5 * N) * S] = ep_return;

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in "" _whL _whM _whO; do
-  echo "variant '$v'"
-  MARBLER_B200_LIB=$PWD/marbler_b200/libmarbler_b200$v.so python scripts/quick_time.py Warehouse 262144 30 2>&1 | tail -1
-done 2>&1 | tee gpurun_out/wh_variants3.log
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "barrier_qp or Warehouse or team_sizes" > gpurun_out/t_wh.log 2>&1; tail -3 gpurun_out/t_wh.log
+for d in -1 0 1; do MRB_HOST_DIRECT=$d python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "host_path or wrapper" 2>&1 | tail -1 | sed "s/^/direct=$d /"; done | tee gpurun_out/t_host.log
+(for c in 2 4 8 16; do MRB_HOST_CHUNKS=$c python scripts/e2e_sweep.py $c 2>&1 | tail -1 | sed "s/^/hybrid /"; done
+MRB_HOST_DIRECT=1 python scripts/e2e_sweep.py 4 2>&1 | tail -1 | sed "s/^/direct=1 /"
+MRB_HOST_DIRECT=0 MRB_HOST_CHUNKS=4 python scripts/e2e_sweep.py 4 2>&1 | tail -1 | sed "s/^/direct=0 /") | tee gpurun_out/e2e_direct.log
+python scripts/e2e_sweep.py 2>&1 | grep raw
