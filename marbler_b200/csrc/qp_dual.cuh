@@ -9,80 +9,101 @@
 // registers.  G G' is never stored: entry (c,d) is +-(a_c . a_d) when the two pairs share a robot.
 #pragma once
 #include "common.cuh"
+#include "qp_store.cuh"
 
 namespace mrb {
 
-template <int N>
+// per-env vectors of the dual solver that may live in the shared store (bit i of VMASK <-> DualVec i); lengths m or n
+enum DualVec { DV_H = 0, DV_RZ, DV_T2, DV_Q, DV_RX, DV_CORR, DV_P, DV_D, DV_S, DV_Z, DV_AX, DV_AY, DV_X, DV_COUNT };
+
+// LS: 1 = the strictly-lower part of the m x m Cholesky factor lives in the shared store as well (the reciprocals
+// of its diagonal stay in registers).  TPB: threads per CTA (the interleave stride of the store).
+template <int N, int TPB = 1, unsigned VMASK = 0, int LS = 0>
 struct QpDual {
     static constexpr int n = 2 * N;
     static constexpr int m = N * (N - 1) / 2;
-    static constexpr int MT = m * (m + 1) / 2;
-    __device__ static constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }   // r >= c
+    static constexpr int MT = m * (m - 1) / 2;                 // strictly-lower entries
+    __device__ static constexpr int low(int r, int c) { return r * (r - 1) / 2 + c; }   // r > c
 
-    double ax[m], ay[m], h[m];
-    double L[MT], invd[m];
+    __device__ static constexpr bool in_smem(int id) { return (VMASK >> id) & 1u; }
+    __device__ static constexpr int len(int id) { return (id == DV_Q || id == DV_RX || id == DV_X) ? n : m; }
+    __device__ static constexpr int offset(int id) { int k = 0; for (int b = 0; b < id; b++) k += in_smem(b) ? len(b) : 0; return k; }
+    static constexpr int kVecDoubles = offset(DV_COUNT);
+    static constexpr int kStoreDoubles = kVecDoubles + (LS ? MT : 0);      // doubles per thread
+    template <int ID> using Vec = MVec<len(ID), TPB, in_smem(ID)>;
 
-    __device__ __forceinline__ void G_mul(const double (&v)[n], double (&out)[m]) const
+    Vec<DV_AX> ax;
+    Vec<DV_AY> ay;
+    MVec<MT, TPB, LS != 0> L;
+    double invd[m];
+    double *Vs;
+
+    __device__ __forceinline__ QpDual(double *Vs_ = nullptr)
+        : ax(Vs_, offset(DV_AX)), ay(Vs_, offset(DV_AY)), L(Vs_, kVecDoubles), Vs(Vs_) {}
+
+    // sink(c, (G v)_c)
+    template <typename V, typename F>
+    __device__ __forceinline__ void G_mul(V &&v, F &&sink) const
     {
         int c = 0;
 #pragma unroll
         for (int i = 0; i < N - 1; i++)
 #pragma unroll
             for (int j = i + 1; j < N; j++, c++)
-                out[c] = ax[c] * (v[2 * j] - v[2 * i]) + ay[c] * (v[2 * j + 1] - v[2 * i + 1]);
+                sink(c, ax.get(c) * (v(2 * j) - v(2 * i)) + ay.get(c) * (v(2 * j + 1) - v(2 * i + 1)));
     }
-    __device__ __forceinline__ void GT_acc(const double (&y)[m], double (&out)[n]) const
+    // out += G' y
+    template <typename F>
+    __device__ __forceinline__ void GT_acc(F &&y, double (&out)[n]) const
     {
         int c = 0;
 #pragma unroll
         for (int i = 0; i < N - 1; i++)
 #pragma unroll
             for (int j = i + 1; j < N; j++, c++) {
-                const double tx = ax[c] * y[c], ty = ay[c] * y[c];
+                const double yc = y(c);
+                const double tx = ax.get(c) * yc, ty = ay.get(c) * yc;
                 out[2 * i] -= tx; out[2 * i + 1] -= ty;
                 out[2 * j] += tx; out[2 * j + 1] += ty;
             }
     }
-    // L := chol(1/2 G G' + diag(d))
-    __device__ __forceinline__ void factor(const double (&d)[m])
+    // entry (c, e), e < c, of 1/2 G G': +-(a_c . a_e)/2 when the two pairs share a robot, else 0
+    template <int C, int E>
+    __device__ __forceinline__ double gram() const
     {
-        {
-            int c = 0;
-#pragma unroll
-            for (int i = 0; i < N - 1; i++)
-#pragma unroll
-                for (int j = i + 1; j < N; j++, c++) {
-                    L[tri(c, c)] = fma(ax[c], ax[c], ay[c] * ay[c]) + d[c];      // 1/2 |g_c|^2 = |a_c|^2
-                    int e = 0;
-#pragma unroll
-                    for (int k = 0; k < N - 1; k++)
-#pragma unroll
-                        for (int l = k + 1; l < N; l++, e++) {
-                            if (e < c) {
-                                const int sgn = (i == k) + (j == l) - (i == l) - (j == k);
-                                if (sgn == 0) L[tri(c, e)] = 0.0;
-                                else {
-                                    const double dot = fma(ax[c], ax[e], ay[c] * ay[e]);
-                                    L[tri(c, e)] = sgn > 0 ? 0.5 * dot : -0.5 * dot;
-                                }
-                            }
-                        }
-                }
+        constexpr int ci = pair_i(C), cj = pair_j(C), ei = pair_i(E), ej = pair_j(E);
+        constexpr int sgn = (ci == ei) + (cj == ej) - (ci == ej) - (cj == ei);
+        if constexpr (sgn == 0) return 0.0;
+        else {
+            const double dot = fma(ax.get(C), ax.get(E), ay.get(C) * ay.get(E));
+            return sgn > 0 ? 0.5 * dot : -0.5 * dot;
         }
-        static_for<0, m>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            double dj = L[tri(j, j)];
+    }
+    __device__ static constexpr int pair_i(int c) { int i = 0; while (c >= N - 1 - i) { c -= N - 1 - i; i++; } return i; }
+    __device__ static constexpr int pair_j(int c) { int i = 0; while (c >= N - 1 - i) { c -= N - 1 - i; i++; } return i + 1 + c; }
+
+    // L := chol(1/2 G G' + diag(d)), row by row: row i is built in registers from the rows above it (each earlier
+    // entry is read once per later row), then stored
+    template <typename D>
+    __device__ __forceinline__ void factor(D &&d)
+    {
+        static_for<0, m>([&](auto I_) {
+            constexpr int i = decltype(I_)::value;
+            double row[i > 0 ? i : 1] = {};
+            static_for<0, i>([&](auto J_) {
+                constexpr int j = decltype(J_)::value;
+                double v = gram<i, j>();
 #pragma unroll
-            for (int k = 0; k < j; k++) dj = fma(-L[tri(j, k)], L[tri(j, k)], dj);
-            const double r = fast_rsqrt(dj);
-            invd[j] = r;
+                for (int k = 0; k < j; k++) v = fma(-row[k], L.get(low(j, k)), v);
+                row[j] = v * invd[j];
+            });
+            const double a = ax.get(i), b = ay.get(i);
+            double dj = fma(a, a, b * b) + d(i);                                   // 1/2 |g_i|^2 = |a_i|^2
 #pragma unroll
-            for (int i = j + 1; i < m; i++) {
-                double v = L[tri(i, j)];
+            for (int k = 0; k < i; k++) dj = fma(-row[k], row[k], dj);
+            invd[i] = fast_rsqrt(dj);
 #pragma unroll
-                for (int k = 0; k < j; k++) v = fma(-L[tri(i, k)], L[tri(j, k)], v);
-                L[tri(i, j)] = v * r;
-            }
+            for (int k = 0; k < i; k++) L.set(low(i, k), row[k]);
         });
     }
     // b := (L L')^-1 b
@@ -92,22 +113,24 @@ struct QpDual {
             constexpr int i = decltype(I)::value;
             double v = b[i];
 #pragma unroll
-            for (int k = 0; k < i; k++) v = fma(-L[tri(i, k)], b[k], v);
+            for (int k = 0; k < i; k++) v = fma(-L.get(low(i, k)), b[k], v);
             b[i] = v * invd[i];
         });
+        // backward sweep in row order: once x_i is known every earlier row receives -L_ik x_i
         static_for<0, m>([&](auto I) {
             constexpr int i = m - 1 - decltype(I)::value;
-            double v = b[i];
+            const double xi = b[i] * invd[i];
+            b[i] = xi;
 #pragma unroll
-            for (int k = i + 1; k < m; k++) v = fma(-L[tri(k, i)], b[k], v);
-            b[i] = v * invd[i];
+            for (int k = 0; k < i; k++) b[k] = fma(-L.get(low(i, k)), xi, b[k]);
         });
     }
 
     __device__ __forceinline__ int run(const double (&xix)[N], const double (&xiy)[N], double (&ux)[N],
                                        double (&uy)[N], bool barrier_default)
     {
-        double q[n], x[n];
+        Vec<DV_Q> q(Vs, offset(DV_Q));
+        Vec<DV_X> x(Vs, offset(DV_X));
 #pragma unroll
         for (int i = 0; i < N; i++) {          // A.8: pre-clip columns of dxi to norm 0.2, f = -2 dxi
             const double n2 = ux[i] * ux[i] + uy[i] * uy[i];
@@ -115,9 +138,19 @@ struct QpDual {
                 const double sc = kQpMagnitudeLimit / sqrt(n2);
                 ux[i] *= sc; uy[i] *= sc;
             }
-            q[2 * i] = -2.0 * ux[i];
-            q[2 * i + 1] = -2.0 * uy[i];
+            q.set(2 * i, -2.0 * ux[i]);
+            q.set(2 * i + 1, -2.0 * uy[i]);
         }
+        Vec<DV_H> h(Vs, offset(DV_H));
+        Vec<DV_S> s(Vs, offset(DV_S));
+        Vec<DV_Z> z(Vs, offset(DV_Z));
+        Vec<DV_RZ> rz(Vs, offset(DV_RZ));
+        Vec<DV_RX> rxs(Vs, offset(DV_RX));
+        Vec<DV_T2> t2(Vs, offset(DV_T2));
+        Vec<DV_D> dd(Vs, offset(DV_D));
+        Vec<DV_CORR> corr(Vs, offset(DV_CORR));
+        Vec<DV_P> pp(Vs, offset(DV_P));
+
         const double r2 = barrier_default ? 0.17 * 0.17 : 0.2 * 0.2;
         double hh = 0.0, qq = 0.0;
         {
@@ -129,75 +162,73 @@ struct QpDual {
                     const double ex = xix[i] - xix[j], ey = xiy[i] - xiy[j];
                     const double hv = (ex * ex + ey * ey) - r2;
                     const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
-                    h[c] = gain * (hv * hv * hv);
-                    ax[c] = 2.0 * ex; ay[c] = 2.0 * ey;
-                    hh = fma(h[c], h[c], hh);
+                    const double hc = gain * (hv * hv * hv);
+                    h.set(c, hc);
+                    ax.set(c, 2.0 * ex); ay.set(c, 2.0 * ey);
+                    hh = fma(hc, hc, hh);
                 }
         }
 #pragma unroll
-        for (int a = 0; a < n; a++) qq = fma(q[a], q[a], qq);
+        for (int a = 0; a < n; a++) { const double qa = q.get(a); qq = fma(qa, qa, qq); }
         // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2
         const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
 
-        double s[m], z[m], t1[m], t2[m];
         // ---- default starting point [P G'; G -I][x; z] = [-q; h]:  (1/2 GG' + I) z = -h - 1/2 G q,  x = -1/2 (q + G'z)
+        factor([](int) { return 1.0; });
+        double tv[m];
+        G_mul([&](int a) { return q.get(a); }, [&](int c, double g) { tv[c] = -h.get(c) - 0.5 * g; });
+        solve(tv);
+        {
+            double xa[n];
 #pragma unroll
-        for (int c = 0; c < m; c++) t1[c] = 1.0;
-        factor(t1);
-        G_mul(q, z);
+            for (int a = 0; a < n; a++) xa[a] = q.get(a);
+            GT_acc([&](int c) { return tv[c]; }, xa);
 #pragma unroll
-        for (int c = 0; c < m; c++) z[c] = -h[c] - 0.5 * z[c];
-        solve(z);
-#pragma unroll
-        for (int a = 0; a < n; a++) x[a] = q[a];
-        GT_acc(z, x);
-#pragma unroll
-        for (int a = 0; a < n; a++) x[a] *= -0.5;
-        G_mul(x, z);                           // z = Gx - h as cvxopt forms it
+            for (int a = 0; a < n; a++) x.set(a, xa[a] * -0.5);
+        }
         double ss = 0.0, ts = -INFINITY, tz = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < m; c++) {
-            z[c] -= h[c];
-            s[c] = -z[c];
-            ss = fma(z[c], z[c], ss);
-            ts = fmax(ts, z[c]);
-            tz = fmax(tz, -z[c]);
-        }
+        G_mul([&](int a) { return x.get(a); }, [&](int c, double g) {       // z = Gx - h as cvxopt forms it
+            const double zc = g - h.get(c);
+            z.set(c, zc);
+            ss = fma(zc, zc, ss);
+            ts = fmax(ts, zc);
+            tz = fmax(tz, -zc);
+        });
         const double nrm = fmax(sqrt(ss), 1.0);
-        if (ts >= -1e-8 * nrm) {
-#pragma unroll
-            for (int c = 0; c < m; c++) s[c] += 1.0 + ts;
-        }
-        if (tz >= -1e-8 * nrm) {
-#pragma unroll
-            for (int c = 0; c < m; c++) z[c] += 1.0 + tz;
-        }
+        const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;
 #pragma unroll
-        for (int c = 0; c < m; c++) gap = fma(s[c], z[c], gap);
+        for (int c = 0; c < m; c++) {
+            const double z0 = z.get(c);
+            double sc = -z0, zc = z0;
+            if (do_s) sc += 1.0 + ts;
+            if (do_z) zc += 1.0 + tz;
+            s.set(c, sc); z.set(c, zc);
+            gap = fma(sc, zc, gap);
+        }
 
         int iters = 0;
         for (; iters <= 50; iters++) {
-            double rx[n], rz[m];
+            double rx[n];
             double xq = 0.0, xrx = 0.0;
 #pragma unroll
             for (int a = 0; a < n; a++) {
-                rx[a] = fma(2.0, x[a], q[a]);
-                xrx = fma(x[a], rx[a], xrx);
-                xq = fma(x[a], q[a], xq);
+                const double xa = x.get(a), qa = q.get(a);
+                rx[a] = fma(2.0, xa, qa);
+                xrx = fma(xa, rx[a], xrx);
+                xq = fma(xa, qa, xq);
             }
             const double f0 = 0.5 * (xrx + xq);
-            GT_acc(z, rx);
-            G_mul(x, rz);
+            GT_acc([&](int c) { return z.get(c); }, rx);
             double resx = 0.0, resz = 0.0, zrz = 0.0;
 #pragma unroll
             for (int a = 0; a < n; a++) resx = fma(rx[a], rx[a], resx);
-#pragma unroll
-            for (int c = 0; c < m; c++) {
-                rz[c] += s[c] - h[c];
-                resz = fma(rz[c], rz[c], resz);
-                zrz = fma(z[c], rz[c], zrz);
-            }
+            G_mul([&](int a) { return x.get(a); }, [&](int c, double g) {
+                const double r = g + (s.get(c) - h.get(c));
+                rz.set(c, r);
+                resz = fma(r, r, resz);
+                zrz = fma(z.get(c), r, zrz);
+            });
             const double pcost = f0, dcost = f0 + zrz - gap;
             // cvxopt's stopping rule without sqrt / division: relgap <= reltol  <=>  gap <= 1e-2 * denominator,
             // pres = sqrt(resz)/resz0 <= feastol  <=>  resz <= (1e-2 * resz0)^2   (equal up to 1 ulp at the threshold)
@@ -206,66 +237,71 @@ struct QpDual {
             else if (dcost > 0.0) gap_ok = gap_ok || (gap <= 1e-2 * dcost);
             if ((resz <= feas_z2 && resx <= feas_x2 && gap_ok) || iters == 50) break;
 
-            double zinv[m], sinv[m], dz[m], ds[m];
+            // 1/s and 1/z are recomputed where they are used (same function of the same input: identical bits)
+            auto inv_s = [&](int c) { return fast_rcp1(s.get(c)); };
+            auto inv_z = [&](int c) { return fast_rcp1(z.get(c)); };
 #pragma unroll
-            for (int c = 0; c < m; c++) {
-                zinv[c] = fast_rcp1(z[c]);
-                sinv[c] = fast_rcp1(s[c]);
-                t1[c] = s[c] * zinv[c];                     // D = s/z
-            }
-            factor(t1);
+            for (int c = 0; c < m; c++) dd.set(c, s.get(c) * inv_z(c));           // D = s/z
+            factor([&](int c) { return dd.get(c); });
             // base right-hand side shared by predictor and corrector: rz - 1/2 G rx - s
-            G_mul(rx, t2);
+            G_mul([&](int a) { return rx[a]; }, [&](int c, double g) { t2.set(c, rz.get(c) - 0.5 * g - s.get(c)); });
 #pragma unroll
-            for (int c = 0; c < m; c++) t2[c] = rz[c] - 0.5 * t2[c] - s[c];
+            for (int a = 0; a < n; a++) rxs.set(a, rx[a]);                          // rx is needed again after the solves
             // predictor (rc = -s.z)
+            double dz[m];
 #pragma unroll
-            for (int c = 0; c < m; c++) dz[c] = t2[c];
+            for (int c = 0; c < m; c++) dz[c] = t2.get(c);
             solve(dz);
             double dsdz = 0.0, tmax = 0.0;
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                ds[c] = -s[c] - t1[c] * dz[c];
-                const double p = ds[c] * dz[c];
+                const double sc = s.get(c);
+                const double dsc = -sc - dd.get(c) * dz[c];
+                const double p = dsc * dz[c];
                 dsdz += p;
-                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
-                ds[c] = p;                                    // keep only the Mehrotra correction term
+                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dz[c] * inv_z(c)));
+                pp.set(c, p);                                  // keep only the Mehrotra correction term
             }
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);          // t == 0 ? 1 : min(1, 1/t)
             const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
             const double sigmamu = sg * sg * sg * (gap / m);
             // corrector (rc = -s.z - ds_aff.dz_aff + sigma mu)
-            double corr[m];
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                corr[c] = (sigmamu - ds[c]) * zinv[c];        // (rc + s.z)/z
-                dz[c] = t2[c] + corr[c];
+                const double cr = (sigmamu - pp.get(c)) * inv_z(c);        // (rc + s.z)/z
+                corr.set(c, cr);
+                dz[c] = t2.get(c) + cr;
             }
             solve(dz);
             tmax = 0.0;
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                ds[c] = corr[c] - s[c] - t1[c] * dz[c];
-                tmax = fmax(tmax, fmax(-ds[c] * sinv[c], -dz[c] * zinv[c]));
+                const double dsc = corr.get(c) - s.get(c) - dd.get(c) * dz[c];
+                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dz[c] * inv_z(c)));
             }
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);          // t == 0 ? 1 : min(1, 0.99/t)
             // dx = -1/2 (rx + G'dz)
-            GT_acc(dz, rx);
+            double rx2[n];
+#pragma unroll
+            for (int a = 0; a < n; a++) rx2[a] = rxs.get(a);
+            GT_acc([&](int c) { return dz[c]; }, rx2);
             const double hstep = -0.5 * step;
 #pragma unroll
-            for (int a = 0; a < n; a++) x[a] = fma(hstep, rx[a], x[a]);
+            for (int a = 0; a < n; a++) x.set(a, fma(hstep, rx2[a], x.get(a)));
             gap = 0.0;
 #pragma unroll
             for (int c = 0; c < m; c++) {
-                s[c] = fma(step, ds[c], s[c]);
-                z[c] = fma(step, dz[c], z[c]);
-                gap = fma(s[c], z[c], gap);
+                const double s0 = s.get(c);
+                const double dsc = corr.get(c) - s0 - dd.get(c) * dz[c];
+                const double sc = fma(step, dsc, s0), zc = fma(step, dz[c], z.get(c));
+                s.set(c, sc); z.set(c, zc);
+                gap = fma(sc, zc, gap);
             }
         }
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            ux[i] = x[2 * i];
-            uy[i] = x[2 * i + 1];
+            ux[i] = x.get(2 * i);
+            uy[i] = x.get(2 * i + 1);
         }
         return iters;
     }

@@ -14,6 +14,7 @@
 //   graph Laplacian of 2x2 blocks  w_c a_c a_c'  -> packed lower-triangular Cholesky, no pivoting.
 #pragma once
 #include "common.cuh"
+#include "qp_store.cuh"
 
 namespace mrb {
 
@@ -30,35 +31,6 @@ namespace mrb {
 // kVecMask (bit order: VecId) live in shared memory, one double per (vector, constraint) interleaved over the
 // threads like the factor; the others are register arrays.
 enum VecId { V_H = 0, V_RZ, V_T2, V_SINV, V_ZINV, V_DS, V_DZ, V_S, V_Z, V_W, V_AX, V_AY, V_COUNT };
-
-template <int LEN, int TPB, bool SHARED>
-struct MVec;
-template <int LEN, int TPB>
-struct MVec<LEN, TPB, false> {
-    double r[LEN];
-    __device__ __forceinline__ MVec(double *, int) {}
-    __device__ __forceinline__ double get(int c) const { return r[c]; }
-    __device__ __forceinline__ void set(int c, double v) { r[c] = v; }
-};
-template <int LEN, int TPB>
-struct MVec<LEN, TPB, true> {
-    double *base;
-    __device__ __forceinline__ MVec(double *vs, int slot) : base(vs + (size_t)slot * LEN * TPB) {}
-    // volatile: without it the compiler merges the repeated loads of one iteration into a single early load and
-    // keeps the value live (then spills it to local memory) -- the opposite of what this store is for
-    __device__ __forceinline__ double get(int c) const { return reinterpret_cast<const volatile double *>(base)[c * TPB]; }
-    __device__ __forceinline__ void set(int c, double v) { reinterpret_cast<volatile double *>(base)[c * TPB] = v; }
-};
-__device__ __forceinline__ void lds_block(uint32_t addr, uint32_t stride, double (&o)[4])
-{
-    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
-    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[2]), "=d"(o[3]) : "r"(addr + stride));
-}
-__device__ __forceinline__ void sts_block(uint32_t addr, uint32_t stride, const double (&o)[4])
-{
-    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(o[0]), "d"(o[1]));
-    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + stride), "d"(o[2]), "d"(o[3]));
-}
 
 // MRB_QP_RECOMPUTE: 1 = 1/s and 1/z are recomputed where they are used (same function of the same input: identical
 // bits) and the corrector's (ds, dz) are recomputed in the update pass instead of being stored: two SFU seeds and
@@ -116,7 +88,7 @@ struct QpThread {
         }
     }
 
-    __device__ __forceinline__ QpThread(double2 *Ls_, double *Vs_) : ax(Vs_, slot(V_AX)), ay(Vs_, slot(V_AY)), Ls((uint32_t)__cvta_generic_to_shared(Ls_)), Vs(Vs_) {}
+    __device__ __forceinline__ QpThread(double2 *Ls_, double *Vs_) : ax(Vs_, slot(V_AX) * MM), ay(Vs_, slot(V_AY) * MM), Ls((uint32_t)__cvta_generic_to_shared(Ls_)), Vs(Vs_) {}
 
     // sink(c, (G v)_c) for every constraint c
     template <typename F>
@@ -257,16 +229,16 @@ struct QpThread {
         }
         if (m == 0) return 0;                  // single robot: u = dxi
 
-        Vec<V_H> h(Vs, slot(V_H));
-        Vec<V_S> s(Vs, slot(V_S));
-        Vec<V_Z> z(Vs, slot(V_Z));
-        Vec<V_RZ> rz(Vs, slot(V_RZ));
-        Vec<V_T2> t2(Vs, slot(V_T2));
-        Vec<V_W> w(Vs, slot(V_W));
-        Vec<V_SINV> sinv(Vs, slot(V_SINV));
-        Vec<V_ZINV> zinv(Vs, slot(V_ZINV));
-        Vec<V_DS> ds(Vs, slot(V_DS));
-        Vec<V_DZ> dz(Vs, slot(V_DZ));
+        Vec<V_H> h(Vs, slot(V_H) * MM);
+        Vec<V_S> s(Vs, slot(V_S) * MM);
+        Vec<V_Z> z(Vs, slot(V_Z) * MM);
+        Vec<V_RZ> rz(Vs, slot(V_RZ) * MM);
+        Vec<V_T2> t2(Vs, slot(V_T2) * MM);
+        Vec<V_W> w(Vs, slot(V_W) * MM);
+        Vec<V_SINV> sinv(Vs, slot(V_SINV) * MM);
+        Vec<V_ZINV> zinv(Vs, slot(V_ZINV) * MM);
+        Vec<V_DS> ds(Vs, slot(V_DS) * MM);
+        Vec<V_DZ> dz(Vs, slot(V_DZ) * MM);
 
         const double r2 = barrier_default ? 0.17 * 0.17 : 0.2 * 0.2;
         double hh = 0.0, qq = 0.0;

@@ -43,28 +43,43 @@ struct ThreadShape {
 #define MRB_QP_SMEM_VECS 0x07      // h, rz, t2
 #endif
 
+// Teams of up to 4 robots (dual QP, qp_dual.cuh): the same choice -- MRB_QPD_SMEM_VECS (bits: DualVec) and
+// MRB_QPD_SMEM_L (the factor) -- together with the CTA shape MRB_THREADS_PER_BLOCK / MRB_MIN_BLOCKS.
+#ifndef MRB_QPD_SMEM_VECS
+#define MRB_QPD_SMEM_VECS 0
+#endif
+#ifndef MRB_QPD_SMEM_L
+#define MRB_QPD_SMEM_L 0
+#endif
+
 // up to 4 robots the constraint-space (dual) Newton system is the smaller one (m <= 6 < 2N)
 template <int N>
-using QpForTeam = std::conditional_t<(N >= 2 && N <= 4), QpDual<N>, QpThread<N, MRB_QP_SMEM_ROWS, ThreadShape<N>::kThreads, MRB_QP_SMEM_VECS>>;
+using QpForTeam = std::conditional_t<(N >= 2 && N <= 4), QpDual<N, ThreadShape<N>::kThreads, MRB_QPD_SMEM_VECS, MRB_QPD_SMEM_L>,
+                                     QpThread<N, MRB_QP_SMEM_ROWS, ThreadShape<N>::kThreads, MRB_QP_SMEM_VECS>>;
 
-// per-CTA shared store of the primal QP: [factor words (double2) | vectors (double)], interleaved over threads
+// per-CTA shared store of the QP: [factor words (double2, primal only) | vectors (double)], interleaved over threads
 template <int N>
 struct QpStore {
     static constexpr bool kPrimal = !(N >= 2 && N <= 4);
+    __host__ __device__ static constexpr int factor_words()
+    {
+        if constexpr (kPrimal) return QpForTeam<N>::kSmemWords;
+        else return 0;
+    }
     __host__ __device__ static constexpr int words()
     {
         if constexpr (kPrimal) return QpForTeam<N>::kSmemWords + (QpForTeam<N>::kVecDoubles + 1) / 2;
-        else return 0;
+        else return (QpForTeam<N>::kStoreDoubles + 1) / 2;
     }
     static constexpr size_t kBytes = (size_t)words() * ThreadShape<N>::kThreads * sizeof(double2);
     double2 *Ls;
     double *Vs;
     __device__ __forceinline__ QpStore() : Ls(nullptr), Vs(nullptr)
     {
-        if constexpr (kPrimal && words() > 0) {
+        if constexpr (words() > 0) {
             extern __shared__ double2 store[];           // words() * threads per CTA, sized by the launcher
             Ls = store + threadIdx.x;
-            Vs = reinterpret_cast<double *>(store + QpForTeam<N>::kSmemWords * ThreadShape<N>::kThreads) + threadIdx.x;
+            Vs = reinterpret_cast<double *>(store + factor_words() * ThreadShape<N>::kThreads) + threadIdx.x;
         }
     }
 };
@@ -73,7 +88,7 @@ __device__ __forceinline__ int qp_run(const double (&xix)[N], const double (&xiy
                                       bool barrier_default, const QpStore<N> &st)
 {
     if constexpr (N >= 2 && N <= 4) {
-        QpForTeam<N> qp;
+        QpForTeam<N> qp(st.Vs);
         return qp.run(xix, xiy, ux, uy, barrier_default);
     } else {
         QpForTeam<N> qp(st.Ls, st.Vs);

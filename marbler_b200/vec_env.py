@@ -111,10 +111,12 @@ class VecEnv(object):
         h = self.host_buffers()
         a = torch.as_tensor(np.asarray(actions), dtype=torch.int32).reshape(self.B, self.N) \
             if not isinstance(actions, torch.Tensor) else actions.to(torch.int32).reshape(self.B, self.N)
-        if a.data_ptr() != h["actions"].data_ptr():
+        # a pinned, contiguous int32 tensor is uploaded from where it is; anything else is staged through h["actions"]
+        if not (a.device.type == "cpu" and a.is_contiguous() and a.is_pinned()):
             h["actions"].copy_(a)
+            a = h["actions"]
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.mrb_step_host(self.handle, _ptr(h["actions"]), _ptr(h["obs"]), _ptr(h["reward"]),
+            _lib.check(self.lib.mrb_step_host(self.handle, _ptr(a), _ptr(h["obs"]), _ptr(h["reward"]),
                                               _ptr(h["done"]), _ptr(h["message"]), self._stream()), self.handle)
         return h["obs"], h["reward"], h["done"], h["message"]
 
