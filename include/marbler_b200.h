@@ -115,7 +115,11 @@ int mrb_step(mrb_env *env, const int32_t *actions, void *cuda_stream);
 /* same step with HOST buffers (pinned for full speed; pageable works): H2D actions, step, D2H
  * obs/reward/done/message, then synchronises.  Batches of >= 16,384 envs are cut into up to 8 chunks,
  * each on its own library-internal stream (ordered after the caller's stream), so that the PCIe copies
- * of one chunk overlap the kernels of the others.  NULL host outputs are skipped. */
+ * of one chunk overlap the kernels of the others.  NULL host outputs are skipped.  When every buffer
+ * is pinned (cudaHostAlloc / cudaHostRegister) the kernel stores reward / done / message directly into
+ * the host buffers through their device aliases and only obs is downloaded by the copy engine;
+ * environment MRB_HOST_DIRECT=1 sends obs the same way, =0 downloads everything.  The device-side
+ * buffers bound with mrb_bind are written in every mode. */
 int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                   uint8_t *done_host, uint8_t *message_host, void *cuda_stream);
 /* unit entry for the barrier-certificate QP alone (rps create_single_integrator_barrier_certificate{,2}

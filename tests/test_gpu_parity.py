@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): discrete outputs (message, done, step counters,
 cells) bit-exact; poses within 1e-5; barrier-QP velocities within 1e-4 of the (restated) cvxopt iterate.
 The measured agreement is ~1e-12, so the tests assert much tighter bounds than the bar where that is
 robust, and the bar itself where float32 outputs are involved."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -255,6 +257,21 @@ def test_host_path_equals_device_path():
     torch.cuda.synchronize()
     assert torch.equal(a_env.obs.cpu(), obs) and torch.equal(a_env.reward.cpu(), rew)
     assert torch.equal(a_env.done.cpu(), done) and torch.equal(a_env.message.cpu(), msg)
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_host_path_output_modes(mode):
+    """mrb_step_host writes the host buffers three ways (include/marbler_b200.h): small outputs stored by the
+    kernel (default, covered by the tests around this one), everything downloaded (MRB_HOST_DIRECT=0) and
+    everything stored by the kernel (=1).  The switch is read once per process, hence the subprocesses."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MRB_HOST_DIRECT=mode)
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                          "test_host_path_equals_device_path or test_chunked_host_path_equals_device_path"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "3 passed" in res.stdout
 
 
 @pytest.mark.parametrize("B", [40000, 70001])

@@ -150,3 +150,17 @@ def test_device_rollout_tracks_host_loop(oracle_lib):
     assert r1._graph is not None
     assert torch.equal(r1.env.state_f64, r2.env.state_f64) and torch.equal(r1.hidden, r2.hidden)
     assert torch.equal(r1.actions, r2.actions) and torch.equal(r1.env.stats, r2.env.stats)
+
+
+@pytest.mark.gpu
+def test_tcgen05_policy_kernel_meets_the_same_bars():
+    """csrc/policy_tc.cuh (tcgen05.mma / TMEM / cp.async.bulk version for hidden 128 + GRUCell, opt-in with
+    MRB_POLICY_TC=1 because it is slower than the mma.sync kernel) must pass the tests above
+    unchanged.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MRB_POLICY_TC="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                          "test_policy_matches_reference_agents or test_fresh_mask or test_device_rollout"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
