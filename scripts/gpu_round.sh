@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-P20="predator=10 capture=10 ROBOT_INIT_RIGHT_THRESH=0.1 num_neighbors=3"
-python scripts/quick_time.py PredatorCapturePrey 32768 5 $P20 2>&1 | tail -1
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "barrier_qp or team_sizes" > gpurun_out/t_w20.log 2>&1; tail -1 gpurun_out/t_w20.log
+S=/usr/local/cuda/bin/compute-sanitizer
+timeout 600 $S --tool memcheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/san_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -c "^ok" gpurun_out/san_memcheck.log; tail -3 gpurun_out/san_memcheck.log
+timeout 900 $S --tool racecheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/san_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -c "^ok" gpurun_out/san_racecheck.log; tail -3 gpurun_out/san_racecheck.log
+MRB_POLICY_TC=1 timeout 600 $S --tool memcheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/san_memcheck_tc.log 2>&1; echo "memcheck tc rc=$?"; tail -3 gpurun_out/san_memcheck_tc.log
