@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "policy_tc.cuh"
+#include "policy_tc2.cuh"
 
 namespace mrb {
 
@@ -292,8 +293,10 @@ struct mrb_policy {
     mrb_policy_desc d;
     int device;
     float *wpack;
-    uint8_t *tc_img;            // tcgen05 path (hidden 128, GRU): canonical FP16 images, NULL otherwise
-    mrb::tc::Params tcp;
+    uint8_t *tc2_img;           // persistent tcgen05 path (policy_tc2.cuh), NULL when the model does not fit it
+    mrb::tc2::Params2 tcp2;
+    size_t tc2_smem;
+    int num_sms;
     PolicyParams p;
     size_t smem_bytes;
     std::string err;
@@ -395,43 +398,54 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
                     }
             }
     }
-    // tcgen05 path: hidden 128 + GRUCell (every shared-weight checkpoint the reference ships)
-    std::vector<uint8_t> tcimg;
-    mrb::tc::Params tcp;
-    std::memset(&tcp, 0, sizeof(tcp));
-    const bool use_tc = H == 128 && d.use_rnn && Din <= mrb::tc::kMaxKp1 && A <= mrb::tc::kNpad2;
-    if (use_tc) {
-        const int Kp1 = (Din + 15) / 16 * 16;
-        const int w1b = Kp1 / 8 * (H / 8 * 128), w2b = H / 8 * (mrb::tc::kNpad2 / 8 * 128), bb = mrb::tc::kBiasFloats * 4;
-        const int headb = w1b + w2b + bb;
-        const int64_t setb = headb + 6LL * mrb::tc::kSlabBytes;
-        tcimg.assign((size_t)setb * sets, 0);
+    // persistent tcgen05 path: head = W1 FP16 [128][dp + 8] | biases | W2 [A][128] as FP32 values rounded to FP16, then twelve
+    // 64 x 128 FP16 half slabs in the order the kernel consumes them (pass, gate r / z / n, W_ih then W_hh)
+    std::vector<uint8_t> tc2img;
+    mrb::tc2::Params2 tcp2;
+    std::memset(&tcp2, 0, sizeof(tcp2));
+    const int dp = (Din + 15) & ~15;
+    const size_t tc2_smem = mrb::tc2::smem_bytes(dp, A);
+    const bool use_tc2 = H == 128 && d.use_rnn && dp <= mrb::tc::kMaxKp1 && A <= mrb::tc2::kMaxA && tc2_smem <= 227 * 1024;
+    if (use_tc2) {
+        const int headf = mrb::tc2::head_floats(dp, A);
+        const int64_t setb = 4LL * headf + (int64_t)mrb::tc2::kSlabsPerTile * mrb::tc2::kHalfSlabBytes;
+        tc2img.assign((size_t)setb * sets, 0);
+        auto r16 = [](float v) { return __half2float(__float2half_rn(v)); };
         for (int sidx = 0; sidx < sets; sidx++) {
             const float *w = weights + per_set * sidx;
             const float *fc1w = w, *fc1b = fc1w + (size_t)H * Din, *wih = fc1b + H, *whh = wih + (size_t)3 * H * H;
             const float *bih = whh + (size_t)3 * H * H, *bhh = bih + 3 * H, *fc2w = bhh + 3 * H, *fc2b = fc2w + (size_t)A * H;
-            uint8_t *o = tcimg.data() + (size_t)setb * sidx;
-            mrb::tc::pack_canonical(o, fc1w, Din, 0, H, Din, H, Kp1);
-            mrb::tc::pack_canonical(o + w1b, fc2w, H, 0, A, H, mrb::tc::kNpad2, H);
-            float *bo = reinterpret_cast<float *>(o + w1b + w2b);
+            uint8_t *o = tc2img.data() + (size_t)setb * sidx;
+            float *hf = reinterpret_cast<float *>(o);
+            __half *w1h = reinterpret_cast<__half *>(o);
+            for (int u = 0; u < H; u++)
+                for (int k = 0; k < Din; k++) w1h[(size_t)u * mrb::tc2::w1_stride(dp) + k] = __float2half_rn(fc1w[(size_t)u * Din + k]);
+            float *bo = hf + mrb::tc2::head_bias(dp);
             std::memcpy(bo, fc1b, sizeof(float) * H);
             std::memcpy(bo + H, bih, sizeof(float) * 3 * H);
             std::memcpy(bo + 4 * H, bhh, sizeof(float) * 3 * H);
             for (int a = 0; a < A; a++) bo[7 * H + a] = fc2b[a];
-            for (int sl = 0; sl < 6; sl++)
-                mrb::tc::pack_canonical(o + headb + (size_t)sl * mrb::tc::kSlabBytes, (sl & 1) ? whh : wih, H, (sl >> 1) * H, H, H, H, H);
+            float *w2 = hf + mrb::tc2::head_w2(dp);
+            for (int a = 0; a < A; a++)
+                for (int k = 0; k < H; k++) w2[(size_t)a * H + k] = r16(fc2w[(size_t)a * H + k]);
+            uint8_t *slabs = o + 4 * (size_t)headf;
+            for (int pass = 0; pass < 2; pass++)
+                for (int g = 0; g < 6; g++)
+                    mrb::tc::pack_canonical(slabs + (size_t)(pass * 6 + g) * mrb::tc2::kHalfSlabBytes, (g & 1) ? whh : wih, H,
+                                            (g >> 1) * H + pass * mrb::tc2::kHalf, mrb::tc2::kHalf, H, mrb::tc2::kHalf, H);
         }
-        tcp.set_bytes = setb; tcp.obs_dim = d.obs_dim; tcp.input_dim = Din; tcp.n_actions = A; tcp.n_agents = N;
-        tcp.obs_agent_id = d.obs_agent_id; tcp.non_shared = d.non_shared; tcp.Kp1 = Kp1;
-        tcp.w1_bytes = w1b; tcp.w2_bytes = w2b; tcp.head_bytes = headb;
+        tcp2.set_bytes = setb; tcp2.obs_dim = d.obs_dim; tcp2.input_dim = Din; tcp2.n_actions = A; tcp2.n_agents = N;
+        tcp2.obs_agent_id = d.obs_agent_id; tcp2.non_shared = d.non_shared; tcp2.dp = dp; tcp2.head_bytes = 4 * headf;
     }
     mrb_policy *pol = new (std::nothrow) mrb_policy();
     if (!pol) return pfail(nullptr, MRB_E_ARG, "mrb_policy_create: out of host memory");
     pol->d = d;
     pol->device = device;
     pol->wpack = nullptr;
-    pol->tc_img = nullptr;
-    pol->tcp = tcp;
+    pol->tc2_img = nullptr;
+    pol->tcp2 = tcp2;
+    pol->tc2_smem = tc2_smem;
+    pol->num_sms = 0;
     if ((st = cudaSetDevice(device)) != cudaSuccess || (st = cudaMalloc(&pol->wpack, img.size() * sizeof(float))) != cudaSuccess ||
         (st = cudaMemcpy(pol->wpack, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
         const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
@@ -439,16 +453,17 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
         delete pol;
         return pfail(nullptr, MRB_E_CUDA, msg);
     }
-    if (use_tc) {
-        if ((st = cudaMalloc(&pol->tc_img, tcimg.size())) != cudaSuccess ||
-            (st = cudaMemcpy(pol->tc_img, tcimg.data(), tcimg.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    if (use_tc2) {
+        if ((st = cudaMalloc(&pol->tc2_img, tc2img.size())) != cudaSuccess ||
+            (st = cudaMemcpy(pol->tc2_img, tc2img.data(), tc2img.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (st = cudaDeviceGetAttribute(&pol->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
             const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
-            if (pol->tc_img) cudaFree(pol->tc_img);
+            if (pol->tc2_img) cudaFree(pol->tc2_img);
             cudaFree(pol->wpack);
             delete pol;
             return pfail(nullptr, MRB_E_CUDA, msg);
         }
-        pol->tcp.img = pol->tc_img;
+        pol->tcp2.img = pol->tc2_img;
     }
     PolicyParams &p = pol->p;
     p.wpack = pol->wpack; p.set_floats = set_floats; p.B = 0;
@@ -465,7 +480,7 @@ extern "C" int mrb_policy_destroy(mrb_policy *p)
     if (!p) return MRB_E_ARG;
     cudaSetDevice(p->device);
     if (p->wpack) cudaFree(p->wpack);
-    if (p->tc_img) cudaFree(p->tc_img);
+    if (p->tc2_img) cudaFree(p->tc2_img);
     delete p;
     return MRB_OK;
 }
@@ -491,15 +506,26 @@ extern "C" int mrb_policy_act(mrb_policy *pol, int64_t num_envs, const float *ob
     PolicyParams p = pol->p;
     p.B = num_envs;
     cudaStream_t s = (cudaStream_t)stream;
-    static const bool tc_on = [] { const char *e = std::getenv("MRB_POLICY_TC"); return e && e[0] == '1'; }();
-    if (pol->tc_img && tc_on) {
-        mrb::tc::Params tp = pol->tcp;
+    // MRB_POLICY_TC=0 forces the mma.sync kernel for models that the persistent tcgen05 kernel covers
+    static const bool tc_off = [] { const char *e = std::getenv("MRB_POLICY_TC"); return e && e[0] == '0'; }();
+    if (pol->tc2_img && !tc_off) {
+        mrb::tc2::Params2 tp = pol->tcp2;
         tp.B = num_envs;
-        if ((st = cudaFuncSetAttribute(mrb::tc::policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mrb::tc::Smem::total)) != cudaSuccess)
-            return pfail(pol, MRB_E_CUDA, std::string("policy kernel attribute: ") + cudaGetErrorString(st));
-        const dim3 grid((unsigned)((num_envs + mrb::tc::kRows - 1) / mrb::tc::kRows), (unsigned)tp.n_agents);
-        mrb::tc::policy_act_tc_kernel<<<grid, mrb::tc::kThreads, mrb::tc::Smem::total, s>>>(tp, obs, hidden, actions, q, fresh);
-        if ((st = cudaGetLastError()) != cudaSuccess) return pfail(pol, MRB_E_CUDA, std::string("policy kernel launch: ") + cudaGetErrorString(st));
+        const int N = tp.n_agents;
+        tp.num_tiles = (int)((num_envs + mrb::tc::kRows - 1) / mrb::tc::kRows) * N;
+        // one persistent CTA per SM; a multiple of n_agents so that a CTA only ever sees one agent index (per-agent
+        // weight sets keep their head resident)
+        int grid = pol->num_sms / N * N;
+        if (grid < N) grid = N;
+        if (grid > tp.num_tiles) grid = tp.num_tiles;
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pol->tc2_smem);
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, mrb::tc2::kThreads2, pol->tc2_smem, s>>>(tp, obs, hidden, actions, q, fresh);
+            return cudaGetLastError();
+        };
+        st = launch(mrb::tc2::policy_act_tc2_kernel);
+        if (st != cudaSuccess) return pfail(pol, MRB_E_CUDA, std::string("policy kernel launch: ") + cudaGetErrorString(st));
         count_launch();
         return MRB_OK;
     }
@@ -512,3 +538,10 @@ extern "C" int mrb_policy_act(mrb_policy *pol, int64_t num_envs, const float *ob
     count_launch();
     return MRB_OK;
 }
+
+#ifdef MRB_TC2_TRACE
+extern "C" int mrb_debug_tc2_trace(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, mrb::tc2::g_tc2_trace, sizeof(unsigned long long) * 256);
+}
+#endif

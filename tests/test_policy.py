@@ -156,13 +156,13 @@ def test_device_rollout_tracks_host_loop(oracle_lib):
 
 
 @pytest.mark.gpu
-def test_tcgen05_policy_kernel_meets_the_same_bars():
-    """csrc/policy_tc.cuh (tcgen05.mma / TMEM / cp.async.bulk version for hidden 128 + GRUCell, opt-in with
-    MRB_POLICY_TC=1 because it is slower than the mma.sync kernel) must pass the tests above
-    unchanged.  The switch is read once per process, hence the subprocess."""
+def test_mma_sync_policy_kernel_meets_the_same_bars():
+    """Models with hidden 128 + GRUCell and <= 8 actions run on the persistent tcgen05 / TMEM kernel
+    (csrc/policy_tc2.cuh) in the tests above; MRB_POLICY_TC=0 sends them to the mma.sync kernel that serves every
+    other model shape, which must pass the same tests.  The switch is read once per process, hence the subprocess."""
     import subprocess
     import sys
-    env = dict(os.environ, MRB_POLICY_TC="1")
+    env = dict(os.environ, MRB_POLICY_TC="0")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
                           "test_policy_matches_reference_agents or test_fresh_mask or test_device_rollout"],
                          env=env, capture_output=True, text=True, timeout=900)
