@@ -215,7 +215,7 @@ def time_rollout(env, steps):
     return {"env_steps_per_s": env.B / (ms * 1e-3), "ms_per_step": ms, "policy_kernel_ms": pol_ms,
             "step_kernel_ms": e2.elapsed_time(e3) / 20, "policy_tflops": flops / (pol_ms * 1e-3) / 1e12,
             "steps": steps, "kernels_per_step": 2, "launch": "CUDA graph replay, 16 env steps per graph",
-            "policy": "RNNAgent hidden 128, GRUCell, obs_agent_id, greedy; FP16 m16n8k16 MMA, FP32 accumulate; random-init weights"}
+            "policy": "RNNAgent hidden 128, GRUCell, obs_agent_id, greedy; persistent tcgen05 / TMEM kernel, FP16 operands, FP32 accumulate; random-init weights"}
 
 
 def run_ours(args):
