@@ -544,4 +544,8 @@ extern "C" int mrb_debug_tc2_trace(unsigned long long *out)
 {
     return (int)cudaMemcpyFromSymbol(out, mrb::tc2::g_tc2_trace, sizeof(unsigned long long) * 256);
 }
+extern "C" int mrb_debug_tc2_trace2(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, mrb::tc2::g_tc2_trace2, sizeof(unsigned long long) * 256);
+}
 #endif

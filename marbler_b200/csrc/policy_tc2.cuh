@@ -121,8 +121,19 @@ __device__ __forceinline__ void trace(int tile, int slot)
     }
 }
 #define TC2_TRACE(tile, slot) trace(tile, slot)
+__device__ unsigned long long g_tc2_trace2[16][16];
+__device__ __forceinline__ void trace2(int tile, int slot)
+{
+    if (blockIdx.x == 0 && tile < 16 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tc2_trace2[tile][slot] = t;
+    }
+}
+#define TC2_TRACE2(tile, slot) trace2(tile, slot)
 #else
 #define TC2_TRACE(tile, slot)
+#define TC2_TRACE2(tile, slot)
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ float round_f16(float v) { return __half2float(__float2half_rn(v)); }
@@ -219,12 +230,14 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
 #pragma unroll
                         for (int i = 0; i < 4; i++) ov[i] = *reinterpret_cast<const float4 *>(hidden + trow[i] * kH + ubn + 4 * tc4);
                     }
+                    if (gi == 0) TC2_TRACE2(n, 0);
                     if (G == 0) {
                         mbar_wait_sleep(tmem_full + 8 * pass, (uint32_t)(n & 1));
                         tc_fence_after();
                         if (tid == 0) TC2_TRACE(n, 1 + 2 * pass);
                     }
                     __syncwarp();
+                    if (gi == 0) TC2_TRACE2(n, 1);
                     const uint32_t tb = lane_base + 256 * pass + kUnitsPerWarp * cq + 16 * G;
 #pragma unroll 1
                     for (int c = 0; c < 2; c++) {
@@ -238,6 +251,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                         const float4 o0 = *reinterpret_cast<const float4 *>(mine), o1 = *reinterpret_cast<const float4 *>(mine + 4);
                         const float old[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
                         tmem_ld_wait();
+                        if (gi == 0) TC2_TRACE2(n, 2 + 3 * c);
                         float hn[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
@@ -247,6 +261,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                             const float nn = tanh_(ai[i] + b_ih[2 * kH + k] + r * (ah[i] + b_hh[2 * kH + k]));
                             hn[i] = (1.f - z) * nn + z * old[i];
                         }
+                        if (gi == 0) TC2_TRACE2(n, 3 + 3 * c);
                         *reinterpret_cast<float4 *>(mine) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                         *reinterpret_cast<float4 *>(mine + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
                         // fc2 partial sums (rnn_agent.py:28) with FP16-rounded operands, like the tensor-core kernels
@@ -263,6 +278,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                                 qacc[a] = s;
                             }
                         }
+                        if (gi == 0) TC2_TRACE2(n, 4 + 3 * c);
                     }
                     if (G == kUnitsPerWarp / 16 - 1) {
                         tc_fence_before();
@@ -276,6 +292,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                         if (tvalid[i])
                             *reinterpret_cast<float4 *>(hidden + trow[i] * kH + ub + 4 * tc4) =
                                 *reinterpret_cast<const float4 *>(tile + (8 * i + tr) * kTileStride + 4 * tc4);
+                    if (gi == 0) TC2_TRACE2(n, 8);
                 }
             }
             // the warps of a row add their parts of fc2 (fixed order), the first one picks the action; the partial sums

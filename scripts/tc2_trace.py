@@ -25,3 +25,10 @@ order = [10, 11, 12, 13, 5, 6, 7, 8, 9, 1, 2, 3, 4]
 print("tile " + " ".join("%15s" % names[k] for k in order))
 for n in range(14):
     print("%4d " % n + " ".join("%15.2f" % ((t[n, k] - t0) / 1e3) for k in order))
+
+L.mrb_debug_tc2_trace2.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
+L.mrb_debug_tc2_trace2(buf)
+t2 = np.array(buf, dtype=np.int64).reshape(16, 16)
+print("epilogue, first group of a tile (us since 'old -> tile'): barrier seen | c0: tmem ready, gates done, fc2 done | c1: ... | stores issued")
+for n in range(4, 12):
+    print("%4d " % n + " ".join("%8.2f" % ((t2[n, k] - t2[n, 0]) / 1e3) for k in range(1, 9)))
