@@ -116,24 +116,9 @@ struct QpWarp {
         __syncwarp();
         const bool me = lane < N;
         const double2 *ri = reinterpret_cast<const double2 *>(blk(me ? lane : 0, 0));
-        for (int j = 0; j < N; j++) {
-            // S = K_ij - sum_{k<j} L_ik L_jk'   (rows i >= j)
-            double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
-            if (me && lane >= j) {
-                const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
-                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
-                sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
-                double txx = 0.0, txy = 0.0, tyx = 0.0, tyy = 0.0;    // second set of accumulators: half the chain length
-                for (int k = 0; k < j; k++) {
-                    const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], j0 = rj[2 * k], j1 = rj[2 * k + 1];
-                    sxx = fma(-i0.x, j0.x, sxx); txx = fma(-i0.y, j0.y, txx);
-                    sxy = fma(-i0.x, j1.x, sxy); txy = fma(-i0.y, j1.y, txy);
-                    syx = fma(-i1.x, j0.x, syx); tyx = fma(-i1.y, j0.y, tyx);
-                    syy = fma(-i1.x, j1.x, syy); tyy = fma(-i1.y, j1.y, tyy);
-                }
-                sxx += txx; sxy += txy; syx += tyx; syy += tyy;
-            }
-            // diagonal block (lane j): L_jj = [l11 0; l21 l22]; every lane runs the arithmetic, lane j's is broadcast
+        // diagonal block from S (every lane runs the arithmetic, lane j's result is broadcast and stored), then
+        // L_ij = S L_jj^-T for the rows below; returns the new block of this lane in (x00, x01, x10, x11)
+        auto finish_column = [&](int j, double sxx, double sxy, double syx, double syy, double &x00, double &x01, double &x10, double &x11) {
             double r1 = fast_rsqrt(sxx);
             double l21 = syx * r1;
             const double d2 = fma(-l21, l21, syy);
@@ -144,12 +129,66 @@ struct QpWarp {
                 invd[2 * j] = r1; invd[2 * j + 1] = r2;
             }
             r1 = __shfl_sync(kFull, r1, j); l21 = __shfl_sync(kFull, l21, j); r2 = __shfl_sync(kFull, r2, j);
-            if (me && lane > j) {                           // L_ij = S L_jj^-T
-                const double x00 = sxx * r1, x10 = syx * r1;
-                const double x01 = fma(-x00, l21, sxy) * r2, x11 = fma(-x10, l21, syy) * r2;
+            x00 = sxx * r1; x10 = syx * r1;
+            x01 = fma(-x00, l21, sxy) * r2; x11 = fma(-x10, l21, syy) * r2;
+            if (me && lane > j) {
                 double2 *o = reinterpret_cast<double2 *>(blk(lane, j));
                 o[0] = make_double2(x00, x01); o[1] = make_double2(x10, x11);
             }
+        };
+        int j = 0;
+        // two block columns per sweep: one load of this lane's block (i,k) feeds the updates of S_ij and S_i,j+1
+        // (16 FMAs per two lane-varying and four broadcast 128-bit loads instead of 8 per two and two)
+        for (; j + 1 < N; j += 2) {
+            double axx = 1.0, axy = 0.0, ayx = 0.0, ayy = 1.0, bxx = 1.0, bxy = 0.0, byx = 0.0, byy = 1.0;
+            if (me && lane >= j) {
+                const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
+                const double2 *rj1 = reinterpret_cast<const double2 *>(blk(j + 1, 0));
+                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
+                axx = a0.x; axy = a0.y; ayx = a1.x; ayy = a1.y;
+                if (lane > j) { const double2 b0 = ri[2 * j + 2], b1 = ri[2 * j + 3]; bxx = b0.x; bxy = b0.y; byx = b1.x; byy = b1.y; }
+                for (int k = 0; k < j; k++) {
+                    const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1], q0 = rj1[2 * k], q1 = rj1[2 * k + 1];
+                    axx = fma(-i0.x, p0.x, axx); axx = fma(-i0.y, p0.y, axx);
+                    axy = fma(-i0.x, p1.x, axy); axy = fma(-i0.y, p1.y, axy);
+                    ayx = fma(-i1.x, p0.x, ayx); ayx = fma(-i1.y, p0.y, ayx);
+                    ayy = fma(-i1.x, p1.x, ayy); ayy = fma(-i1.y, p1.y, ayy);
+                    bxx = fma(-i0.x, q0.x, bxx); bxx = fma(-i0.y, q0.y, bxx);
+                    bxy = fma(-i0.x, q1.x, bxy); bxy = fma(-i0.y, q1.y, bxy);
+                    byx = fma(-i1.x, q0.x, byx); byx = fma(-i1.y, q0.y, byx);
+                    byy = fma(-i1.x, q1.x, byy); byy = fma(-i1.y, q1.y, byy);
+                }
+            }
+            double x00, x01, x10, x11;
+            finish_column(j, axx, axy, ayx, ayy, x00, x01, x10, x11);
+            // the k = j term of column j + 1 needs L_(j+1),j, which lane j + 1 has just computed
+            const double t00 = __shfl_sync(kFull, x00, j + 1), t01 = __shfl_sync(kFull, x01, j + 1);
+            const double t10 = __shfl_sync(kFull, x10, j + 1), t11 = __shfl_sync(kFull, x11, j + 1);
+            bxx = fma(-x00, t00, bxx); bxx = fma(-x01, t01, bxx);
+            bxy = fma(-x00, t10, bxy); bxy = fma(-x01, t11, bxy);
+            byx = fma(-x10, t00, byx); byx = fma(-x11, t01, byx);
+            byy = fma(-x10, t10, byy); byy = fma(-x11, t11, byy);
+            if (!(me && lane > j)) { bxx = 1.0; bxy = 0.0; byx = 0.0; byy = 1.0; }      // lanes without a row in column j + 1
+            double y00, y01, y10, y11;
+            finish_column(j + 1, bxx, bxy, byx, byy, y00, y01, y10, y11);
+            __syncwarp();
+        }
+        if (j < N) {                                        // odd team size: the last block column on its own
+            double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
+            if (me && lane >= j) {
+                const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
+                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
+                sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
+                for (int k = 0; k < j; k++) {
+                    const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1];
+                    sxx = fma(-i0.x, p0.x, sxx); sxx = fma(-i0.y, p0.y, sxx);
+                    sxy = fma(-i0.x, p1.x, sxy); sxy = fma(-i0.y, p1.y, sxy);
+                    syx = fma(-i1.x, p0.x, syx); syx = fma(-i1.y, p0.y, syx);
+                    syy = fma(-i1.x, p1.x, syy); syy = fma(-i1.y, p1.y, syy);
+                }
+            }
+            double x00, x01, x10, x11;
+            finish_column(j, sxx, sxy, syx, syy, x00, x01, x10, x11);
             __syncwarp();
         }
     }
