@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py tests/test_qp_crosscheck.py -m gpu -x -q -k "barrier_qp or team_sizes or fixture or full_size or crosscheck or qp" > gpurun_out/t_w20.log 2>&1; tail -2 gpurun_out/t_w20.log
-P20="predator=10 capture=10 ROBOT_INIT_RIGHT_THRESH=0.1 num_neighbors=3"
-python scripts/quick_time.py PredatorCapturePrey 32768 5 $P20 2>&1 | tail -1
-python scripts/quick_time.py PredatorCapturePrey 32768 5 predator=4 capture=5 ROBOT_INIT_RIGHT_THRESH=0.1 num_neighbors=3 2>&1 | tail -1
+P20="--override predator=10 --override capture=10 --override ROBOT_INIT_RIGHT_THRESH=0.1 --override num_neighbors=3"
+python bench.py --envs 131072 --steps 10 --warmup 3 $P20 > gpurun_out/bench_pcp20_r5.json 2> gpurun_out/bench_pcp20_r5.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_pcp20_r5.json').read().strip().split('\n')[-1]); print('pcp20', d['ms_per_step'], d['value'], d['e2e']['value'], d['cpu_baseline']['value'])"
+ncu --set full --import-source on --clock-control none -k regex:step_warp -c 1 -o gpurun_out/ncu_pcp20e python bench.py --envs 16384 --steps 1 --warmup 3 --no-cpu-baseline $P20 > gpurun_out/ncu_pcp20e.log 2>&1
