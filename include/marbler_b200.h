@@ -132,8 +132,9 @@ int mrb_barrier_qp(int device, int32_t num_robots, int32_t barrier_default, int6
  * (run_env) calls utilities/rnn_agent.py:5-29 RNNAgent / utilities/rnn_ns_agent.py:5-36 RNNNSAgent on the
  * host once per env step: q, h = model(obs, h); actions = argmax(q).  mrb_policy_act does that for every
  * agent of every env in one kernel: fc1 -> ReLU -> GRUCell (or Linear+ReLU when use_rnn == 0) -> fc2 ->
- * greedy argmax, TF32 tensor-core MMA with FP32 accumulation, reading the env's obs buffer and writing
- * the actions buffer mrb_step consumes (no host round trip). */
+ * greedy argmax, tensor-core MMAs on FP16 operands with FP32 accumulation and FP32 gates (tcgen05 / TMEM for
+ * hidden 128 + GRUCell with <= 8 actions, mma.sync otherwise), reading the env's obs buffer and writing the
+ * actions buffer mrb_step consumes (no host round trip). */
 typedef struct mrb_policy_desc {
     int32_t struct_size;        /* sizeof(mrb_policy_desc): ABI check */
     int32_t obs_dim;            /* D: width of one agent's row in the obs buffer */
