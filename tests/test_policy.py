@@ -164,6 +164,54 @@ def test_mma_sync_policy_kernel_meets_the_same_bars():
     import sys
     env = dict(os.environ, MRB_POLICY_TC="0")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
-                          "test_policy_matches_reference_agents or test_fresh_mask or test_device_rollout"],
+                          "test_policy_matches_reference_agents or test_fresh_mask or test_device_rollout or test_hidden128"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def _emulated_forward(sd, prefix, obs, h):
+    """RNNAgent.forward (utilities/rnn_agent.py:21-29) in float32 torch with the matmul operands rounded to FP16 -
+    the arithmetic contract of both policy kernels."""
+    r16 = lambda t: t.half().float()
+    g = lambda k: torch.as_tensor(sd[prefix + k], device=obs.device)
+    H = g("fc1.weight").shape[0]
+    x = torch.relu(r16(obs) @ r16(g("fc1.weight")).T + g("fc1.bias"))
+    gi = r16(x) @ r16(g("rnn.weight_ih")).T + g("rnn.bias_ih")
+    gh = r16(h) @ r16(g("rnn.weight_hh")).T + g("rnn.bias_hh")
+    r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+    z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+    n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+    hn = (1 - z) * n + z * h
+    return r16(hn) @ r16(g("fc2.weight")).T + g("fc2.bias"), hn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("non_shared,B", [(True, 1000), (False, 777)])
+def test_hidden128_gru_models_per_agent_and_shared(non_shared, B):
+    """The reference ships no RNNNSAgent checkpoint with hidden 128 + GRUCell, the shape the persistent tcgen05 kernel
+    serves with per-agent weight sets (one agent index per CTA): random weights, ragged last tile, three steps of
+    recurrence, against the emulated float32 forward above."""
+    from marbler_b200.policy import Policy
+    rng = np.random.RandomState(5)
+    N, D, A, H = 3, 11, 6, 128
+    shapes = {"fc1.weight": (H, D), "fc1.bias": (H,), "rnn.weight_ih": (3 * H, H), "rnn.weight_hh": (3 * H, H),
+              "rnn.bias_ih": (3 * H,), "rnn.bias_hh": (3 * H,), "fc2.weight": (A, H), "fc2.bias": (A,)}
+    prefixes = ["agents.%d." % i for i in range(N)] if non_shared else [""]
+    sd = {p + k: (rng.standard_normal(s) / np.sqrt(s[-1] if len(s) > 1 else 16)).astype(np.float32) for p in prefixes for k, s in shapes.items()}
+    pol = Policy(sd, N, D, obs_agent_id=False, device="cuda:0")
+    hidden = pol.init_hidden(B)
+    h_ref = torch.zeros((B, N, H), device="cuda:0")
+    q = torch.zeros((B, N, A), device="cuda:0")
+    for t in range(3):
+        obs = torch.as_tensor(rng.standard_normal((B, N, D)).astype(np.float32), device="cuda:0")
+        a = pol.act(obs, hidden, q=q)
+        torch.cuda.synchronize()
+        for i in range(N):
+            qr, hr = _emulated_forward(sd, prefixes[i if non_shared else 0], obs[:, i], h_ref[:, i])
+            h_ref[:, i] = hr
+            scale = float(qr.abs().max())
+            assert float((q[:, i] - qr).abs().max()) < 2e-4 * scale + 2e-4, (t, i)
+            top = torch.sort(qr, dim=1).values
+            clear = (top[:, -1] - top[:, -2]) > 1e-3 * scale
+            assert torch.equal(a[:, i][clear].long(), qr.argmax(dim=1)[clear]), (t, i)
+        assert float((hidden - h_ref).abs().max()) < 1e-3
