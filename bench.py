@@ -218,6 +218,25 @@ def time_rollout(env, steps):
             "policy": "RNNAgent hidden 128, GRUCell, obs_agent_id, greedy; persistent tcgen05 / TMEM kernel, FP16 operands, FP32 accumulate; random-init weights"}
 
 
+def fp64_pipe_from_profile(scenario, B):
+    """FP64-pipe utilisation of the step kernel from the committed ncu capture of this workload (a profiler number,
+    quoted beside the live timing, never measured under it): the roofline that binds."""
+    name = {("PredatorCapturePrey", 65536): "r01_ncu_step_thread_pcp4_final_raw.csv",
+            ("Warehouse", 262144): "r01_ncu_step_thread_wh6_smemfactor_raw.csv"}.get((scenario, B))
+    if name is None:
+        return {}
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        d = dict(zip(rows[0], rows[2]))
+        return {"pipe_pct_of_peak": float(d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]),
+                "issue_slots_pct": float(d["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]),
+                "pipe_source": "profiles/" + name}
+    except Exception:
+        return {}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -330,9 +349,9 @@ def run_ours(args):
                      "kernel": "step_thread_kernel<%s,%d>" % (args.scenario, env.N),
                      "note": "the step is FP64-issue bound, not HBM bound (SURVEY 8d, DESIGN.md section 5); "
                              "fp64 object below is the binding roofline"},
-        "fp64": {"ipm_iterations_per_solve": stats["qp_iters_per_solve"],
-                 "qp_solves_per_env_step": stats["qp_solves"] / max(stats["env_steps"], 1.0),
-                 "qp_stalls": stats["qp_stalls"]},
+        "fp64": dict({"ipm_iterations_per_solve": stats["qp_iters_per_solve"],
+                      "qp_solves_per_env_step": stats["qp_solves"] / max(stats["env_steps"], 1.0),
+                      "qp_stalls": stats["qp_stalls"]}, **fp64_pipe_from_profile(args.scenario, B)),
         "episodes": {k: stats[k] for k in ("episodes", "return_mean", "length_mean", "collisions", "boundary_exits", "timeouts")},
         "clocks": clocks,
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
