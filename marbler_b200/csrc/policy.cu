@@ -405,7 +405,7 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
     std::memset(&tcp2, 0, sizeof(tcp2));
     const int dp = (Din + 15) & ~15;
     const size_t tc2_smem = mrb::tc2::smem_bytes(dp, A);
-    const bool use_tc2 = H == 128 && d.use_rnn && dp <= mrb::tc::kMaxKp1 && A <= mrb::tc2::kMaxA && tc2_smem <= 227 * 1024;
+    const bool use_tc2 = H == 128 && d.use_rnn && dp <= mrb::tc::kMaxKp1 && A <= mrb::tc2::kMaxA && mrb::tc2::ring_depth(dp, A) >= 2;
     if (use_tc2) {
         const int headf = mrb::tc2::head_floats(dp, A);
         const int64_t setb = 4LL * headf + (int64_t)mrb::tc2::kSlabsPerTile * mrb::tc2::kHalfSlabBytes;
@@ -436,6 +436,7 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
         }
         tcp2.set_bytes = setb; tcp2.obs_dim = d.obs_dim; tcp2.input_dim = Din; tcp2.n_actions = A; tcp2.n_agents = N;
         tcp2.obs_agent_id = d.obs_agent_id; tcp2.non_shared = d.non_shared; tcp2.dp = dp; tcp2.head_bytes = 4 * headf;
+        tcp2.ring_off = mrb::tc2::ring_offset(dp, A); tcp2.ring = mrb::tc2::ring_depth(dp, A);
     }
     mrb_policy *pol = new (std::nothrow) mrb_policy();
     if (!pol) return pfail(nullptr, MRB_E_ARG, "mrb_policy_create: out of host memory");

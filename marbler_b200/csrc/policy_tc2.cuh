@@ -12,7 +12,7 @@
 //                      mma.sync.m16n8k16 (K <= 64: 1 % of the flops; a tcgen05 fc1 would need a MMA -> epilogue -> MMA
 //                      round trip per tile and TMEM columns that the two gate halves occupy); two activation buffers
 //   loader    1 thread streams the GRU weights as twelve 64 x 128 FP16 half slabs per tile (cp.async.bulk, 1-D: the
-//                      host packed them in the canonical layout) through a three-deep 16 KB ring
+//                      host packed them in the canonical layout) through a three-deep (two when shared memory is short) 16 KB ring
 //   mma       1 thread per tile two half passes of 64 hidden units; a pass is 6 slabs x 8 tcgen05.mma (M 128, N 64,
 //                      K 16) into one 256-column half of TMEM: r -> [0,64), z -> [64,128), W_in x -> [128,192),
 //                      W_hn h -> [192,256); tcgen05.commit releases slabs, activation buffers and TMEM halves
@@ -32,7 +32,7 @@ using namespace mrb::tc;
 constexpr int kHalf = 64;                                  // hidden units per pass
 constexpr int kHalfSlabBytes = kHalf * kH * 2;             // 16 KB
 constexpr int kSlabsPerTile = 12;                          // 2 passes x (W_ir, W_hr, W_iz, W_hz, W_in, W_hn)
-constexpr int kRing2 = 3;
+constexpr int kRingMax = 3;                               // weight-ring slots: 3 when they fit, else 2 (Params2::ring)
 #ifndef MRB_TC2_EPI_WARPS
 #define MRB_TC2_EPI_WARPS 8
 #endif
@@ -51,6 +51,7 @@ struct Params2 {
     int32_t dp;               // input_dim rounded up to a multiple of 16 (fc1 k extent)
     int32_t head_bytes;       // W1 f16 [128][dp + 8] | b1 | b_ih | b_hh | b2 [32] | W2 f32 [n_actions][128] (FP16-rounded values)
     int32_t num_tiles;        // ceil(B / 128) * n_agents
+    int32_t ring_off, ring;   // byte offset and depth of the weight ring (after everything else in shared memory)
 };
 
 // head offsets in floats; W1 rows are dp + 8 halves long: the 16-byte pad spreads the B-fragment loads over the banks
@@ -62,20 +63,27 @@ __host__ __device__ inline int head_floats(int dp, int n_actions) { return head_
 struct Smem2 {
     static constexpr int act = 0;                                    // 2 x (x | h)
     static constexpr int act_stride = 2 * kActBytes;
-    static constexpr int ring = act + 2 * act_stride;
-    static constexpr int bars = ring + kRing2 * kHalfSlabBytes;      // act_full[2] act_free[2] slab_full[3] slab_empty[3] tmem_full[2] tmem_free[2] head
+    static constexpr int bars = act + 2 * act_stride;                // act_full[2] act_free[2] slab_full[3] slab_empty[3] tmem_full[2] tmem_free[2] head
     static constexpr int tmem_slot = bars + 16 * 8;
     static constexpr int head = tmem_slot + 64;
 };
-// after the head: one 32-row x 16-unit exchange tile per epilogue warp (old hidden state in, h' out, fc2 partial sums)
-__host__ __device__ inline int ap_of(int) { return kMaxA; }
-// ... and one 16-row x (dp + 8) FP16 scratch per staging warp for the A fragments of fc1
+// after the head: one 32-row x 16-unit exchange tile per epilogue warp (old hidden state in, h' out, fc2 partial sums),
+// one 16-row x (dp + 8) FP16 scratch per staging warp for the A fragments of fc1, then the weight ring
 __host__ __device__ inline int scratch_halves(int dp) { return 16 * w1_stride(dp); }
-__host__ inline size_t smem_bytes(int dp, int n_actions)
+__host__ inline int ring_offset(int dp, int n_actions)
 {
-    return (size_t)Smem2::head + 4 * (size_t)head_floats(dp, n_actions) + 4 * (size_t)kEpiWarps * 32 * kTileStride +
-           2 * (size_t)kStageWarps * scratch_halves(dp);
+    const size_t end = (size_t)Smem2::head + 4 * (size_t)head_floats(dp, n_actions) + 4 * (size_t)kEpiWarps * 32 * kTileStride +
+                       2 * (size_t)kStageWarps * scratch_halves(dp);
+    return (int)((end + 127) & ~(size_t)127);
 }
+// deepest ring that fits the 227 KB a CTA may use (0: the model does not fit this kernel)
+__host__ inline int ring_depth(int dp, int n_actions)
+{
+    for (int r = kRingMax; r >= 2; r--)
+        if ((size_t)ring_offset(dp, n_actions) + (size_t)r * kHalfSlabBytes <= 227 * 1024) return r;
+    return 0;
+}
+__host__ inline size_t smem_bytes(int dp, int n_actions) { return (size_t)ring_offset(dp, n_actions) + (size_t)ring_depth(dp, n_actions) * kHalfSlabBytes; }
 // D = A (16x16, row) * B (16x8, col) + D, FP16 inputs, FP32 accumulate
 __device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
@@ -152,6 +160,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + Smem2::tmem_slot);
     const int N = p.n_agents, D = p.obs_dim, Din = p.input_dim, A = p.n_actions, Dp = p.dp;
     constexpr int AP = kMaxA;                                   // action accumulators per epilogue thread (>= A)
+    const uint32_t ring = (uint32_t)p.ring;
     const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == kEpiWarps) {                                    // the MMA warp owns the TMEM allocation
@@ -165,7 +174,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
             mbar_init(tmem_full + 8 * i, 1);
             mbar_init(tmem_free + 8 * i, kEpiWarps * 32);
         }
-        for (int i = 0; i < kRing2; i++) { mbar_init(slab_full + 8 * i, 1); mbar_init(slab_empty + 8 * i, 1); }
+        for (int i = 0; i < kRingMax; i++) { mbar_init(slab_full + 8 * i, 1); mbar_init(slab_empty + 8 * i, 1); }
         mbar_init(head_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -337,15 +346,15 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                     tc_fence_after();
                     TC2_TRACE(n, 6 + 2 * pass);
                     for (int g = 0; g < 6; g++, q++) {
-                        const uint32_t slot = q % kRing2;
-                        mbar_wait(slab_full + 8 * slot, (q / kRing2) & 1);
+                        const uint32_t slot = q % ring;
+                        mbar_wait(slab_full + 8 * slot, (q / ring) & 1);
                         tc_fence_after();
                         const uint32_t a_base = (g & 1) ? ha : xa;                          // even slabs multiply x, odd slabs h
                         const uint32_t d_col = 256u * pass + (g < 4 ? 64u * (g >> 1) : 64u * (g - 2));   // r, r, z, z, in, hn
                         const uint32_t acc0 = (g == 1 || g == 3) ? 1u : 0u;                 // the h side of r and z accumulates
                         for (int ks = 0; ks < kH / 16; ks++) {
                             const uint64_t ad = make_desc(a_base + ks * 2 * kActLBO, kActLBO, 128);
-                            const uint64_t bd = make_desc(sbase + Smem2::ring + slot * kHalfSlabBytes + ks * 2 * (kHalf / 8 * 128), kHalf / 8 * 128, 128);
+                            const uint64_t bd = make_desc(sbase + p.ring_off + slot * kHalfSlabBytes + ks * 2 * (kHalf / 8 * 128), kHalf / 8 * 128, 128);
                             umma(tmem + d_col, ad, bd, idesc, acc0 | (ks > 0));
                         }
                         tc_commit(slab_empty + 8 * slot);
@@ -367,10 +376,10 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                 const int t = (int)blockIdx.x + n * (int)gridDim.x;
                 const uint8_t *img = p.img + (size_t)(p.non_shared ? (t % N) : 0) * p.set_bytes + p.head_bytes;
                 for (int s = 0; s < kSlabsPerTile; s++, q++) {
-                    const uint32_t slot = q % kRing2;
-                    mbar_wait(slab_empty + 8 * slot, ((q / kRing2) & 1) ^ 1);
+                    const uint32_t slot = q % ring;
+                    mbar_wait(slab_empty + 8 * slot, ((q / ring) & 1) ^ 1);
                     mbar_expect_tx(slab_full + 8 * slot, kHalfSlabBytes);
-                    bulk_g2s(sbase + Smem2::ring + slot * kHalfSlabBytes, img + (size_t)s * kHalfSlabBytes, kHalfSlabBytes, slab_full + 8 * slot);
+                    bulk_g2s(sbase + p.ring_off + slot * kHalfSlabBytes, img + (size_t)s * kHalfSlabBytes, kHalfSlabBytes, slab_full + 8 * slot);
                 }
             }
         }

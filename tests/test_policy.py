@@ -186,19 +186,21 @@ def _emulated_forward(sd, prefix, obs, h):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("non_shared,B", [(True, 1000), (False, 777)])
-def test_hidden128_gru_models_per_agent_and_shared(non_shared, B):
+@pytest.mark.parametrize("non_shared,B,D,agent_id", [(True, 1000, 11, False), (False, 777, 11, False), (False, 300, 30, True)])
+def test_hidden128_gru_models_per_agent_and_shared(non_shared, B, D, agent_id):
     """The reference ships no RNNNSAgent checkpoint with hidden 128 + GRUCell, the shape the persistent tcgen05 kernel
     serves with per-agent weight sets (one agent index per CTA): random weights, ragged last tile, three steps of
-    recurrence, against the emulated float32 forward above."""
+    recurrence, against the emulated float32 forward above.  The 30-wide observation + one-hot id is ArcticTransport's
+    input (fc1 k extent 48: the kernel then runs with a two-deep weight ring)."""
     from marbler_b200.policy import Policy
     rng = np.random.RandomState(5)
-    N, D, A, H = 3, 11, 6, 128
-    shapes = {"fc1.weight": (H, D), "fc1.bias": (H,), "rnn.weight_ih": (3 * H, H), "rnn.weight_hh": (3 * H, H),
+    N, A, H = (4 if agent_id else 3), 6, 128
+    Din = D + (N if agent_id else 0)
+    shapes = {"fc1.weight": (H, Din), "fc1.bias": (H,), "rnn.weight_ih": (3 * H, H), "rnn.weight_hh": (3 * H, H),
               "rnn.bias_ih": (3 * H,), "rnn.bias_hh": (3 * H,), "fc2.weight": (A, H), "fc2.bias": (A,)}
     prefixes = ["agents.%d." % i for i in range(N)] if non_shared else [""]
     sd = {p + k: (rng.standard_normal(s) / np.sqrt(s[-1] if len(s) > 1 else 16)).astype(np.float32) for p in prefixes for k, s in shapes.items()}
-    pol = Policy(sd, N, D, obs_agent_id=False, device="cuda:0")
+    pol = Policy(sd, N, D, obs_agent_id=agent_id, device="cuda:0")
     hidden = pol.init_hidden(B)
     h_ref = torch.zeros((B, N, H), device="cuda:0")
     q = torch.zeros((B, N, A), device="cuda:0")
@@ -207,7 +209,11 @@ def test_hidden128_gru_models_per_agent_and_shared(non_shared, B):
         a = pol.act(obs, hidden, q=q)
         torch.cuda.synchronize()
         for i in range(N):
-            qr, hr = _emulated_forward(sd, prefixes[i if non_shared else 0], obs[:, i], h_ref[:, i])
+            x = obs[:, i]
+            if agent_id:                                   # utilities/misc.py:161-162
+                onehot = torch.zeros((B, N), device="cuda:0"); onehot[:, i] = 1.0
+                x = torch.cat([x, onehot], dim=1)
+            qr, hr = _emulated_forward(sd, prefixes[i if non_shared else 0], x, h_ref[:, i])
             h_ref[:, i] = hr
             scale = float(qr.abs().max())
             assert float((q[:, i] - qr).abs().max()) < 2e-4 * scale + 2e-4, (t, i)
