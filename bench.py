@@ -222,7 +222,7 @@ def fp64_pipe_from_profile(scenario, B):
     """FP64-pipe utilisation of the step kernel from the committed ncu capture of this workload (a profiler number,
     quoted beside the live timing, never measured under it): the roofline that binds."""
     name = {("PredatorCapturePrey", 65536): "r01_ncu_step_thread_pcp4_final_raw.csv",
-            ("Warehouse", 262144): "r01_ncu_step_thread_wh6_smemfactor_raw.csv"}.get((scenario, B))
+            ("Warehouse", 262144): "r01_ncu_step_thread_wh6_cta256_raw.csv"}.get((scenario, B))
     if name is None:
         return {}
     path = os.path.join(ROOT, "profiles", name)

@@ -21,10 +21,10 @@ namespace mrb {
 #endif
 // teams of 5 and 6 robots: the CTA shape is set by the shared-memory QP store (see below), not by registers
 #ifndef MRB_THREADS_PER_BLOCK_PRIMAL
-#define MRB_THREADS_PER_BLOCK_PRIMAL 64
+#define MRB_THREADS_PER_BLOCK_PRIMAL 256     // one 8-warp CTA per SM: its warps run the 12 k-instruction body in step and share the instruction fetches
 #endif
 #ifndef MRB_MIN_BLOCKS_PRIMAL
-#define MRB_MIN_BLOCKS_PRIMAL 4
+#define MRB_MIN_BLOCKS_PRIMAL 1
 #endif
 template <int N>
 struct ThreadShape {
@@ -40,7 +40,7 @@ struct ThreadShape {
 #define MRB_QP_SMEM_ROWS 6
 #endif
 #ifndef MRB_QP_SMEM_VECS
-#define MRB_QP_SMEM_VECS 0x07      // h, rz, t2
+#define MRB_QP_SMEM_VECS 0x03      // h, rz
 #endif
 
 // Teams of up to 4 robots (dual QP, qp_dual.cuh): the same choice -- MRB_QPD_SMEM_VECS (bits: DualVec) and
