@@ -51,7 +51,7 @@ static cudaError_t launch_qp_thread(int64_t B, int barrier_default, const double
     constexpr int tpb = ThreadShape<N>::kThreads;
     const unsigned grid = (unsigned)((B + tpb - 1) / tpb);
     if (smem > 48 * 1024) {
-        static cudaError_t attr = cudaFuncSetAttribute(qp_thread_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t attr = cudaFuncSetAttribute(qp_thread_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (attr != cudaSuccess) return attr;
     }
     qp_thread_kernel<N><<<grid, tpb, smem, s>>>(B, barrier_default, dxi, xi, u, iters);

@@ -13,7 +13,7 @@ inline cudaError_t launch_thread(const Params &p, const int32_t *actions, cudaSt
     const unsigned grid = (unsigned)((p.env_hi - p.env_lo + tpb - 1) / tpb);
     constexpr size_t smem = QpStore<N>::kBytes;
     if (smem > 48 * 1024) {
-        static cudaError_t attr = cudaFuncSetAttribute(step_thread_kernel<SCN, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t attr = cudaFuncSetAttribute(step_thread_kernel<SCN, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (attr != cudaSuccess) return attr;
     }
     step_thread_kernel<SCN, N><<<grid, tpb, smem, s>>>(p, actions);
