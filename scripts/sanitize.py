@@ -24,7 +24,6 @@ def run(scn, B, over=None, steps=3, host=False):
 
 for scn in ("PredatorCapturePrey", "Warehouse", "MaterialTransport", "ArcticTransport", "Simple"):
     run(scn, 200)
-run("Warehouse", 100, dict(n_agents=5) if False else None)
 run("PredatorCapturePrey", 40, dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
 run("PredatorCapturePrey", 70, dict(predator=4, capture=4, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
 run("PredatorCapturePrey", 33000, host=True, steps=2)
