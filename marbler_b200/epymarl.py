@@ -18,6 +18,14 @@ env axis and stays a CUDA tensor (`reward [B]`, `terminated [B]`, `obs [B, N, D]
 parallel runner.  With `num_envs == 1` the return types are EPyMARL's own (float, bool, list of numpy
 arrays), i.e. it is a drop-in for `_GymmaWrapper`.  Envs that finish (own `done` or the time limit) are
 re-sampled in place before the next step; `episode_limit` truncation resets them through `mrb_reset`'s mask.
+
+Episode boundaries in the batched mode (both ways of finishing behave the same): after `step()`, `get_obs()` /
+`get_state()` hold the TERMINAL observation of every env that just finished (what EPyMARL's runners store as
+the last transition of the episode) - a private copy, so the masked re-sampling that follows (which zeroes
+the reset envs' rows of the device obs buffer, like the reference's `reset()` returning zeros) cannot touch
+it.  `info["fresh"]` / `fresh_mask()` flag those envs: they start a new episode at the next step, and
+`get_obs(episode_start=True)` / `get_state(episode_start=True)` return the buffer with their rows zeroed,
+i.e. exactly what the reference's `reset()` would have handed the learner as the first observation.
 """
 import numpy as np
 import torch
@@ -47,6 +55,7 @@ class GymmaVecEnv(object):
         self._obs = None
         self._elapsed = None
         self._truncated = None
+        self._fresh = None
 
     # ------------------------------------------------------------------ helpers
     def _pad(self, obs):
@@ -76,16 +85,27 @@ class GymmaVecEnv(object):
         self._truncated = limit & ~terminated
         terminated |= limit
         team_reward = reward.sum(dim=1)
-        self._obs = self._pad(obs)
+        # private copy: `obs` is the env's device buffer, and the masked reset below zeroes the rows of the envs it
+        # re-samples - the terminal observations must survive it (own-done envs keep theirs in the buffer too)
+        self._obs = self._pad(obs).clone()
+        self._fresh = terminated
         # own-done envs were re-sampled inside the step kernel (auto-reset); truncated ones are reset here
         if bool(self._truncated.any()):
             self._env.reset(mask=self._truncated)
         self._elapsed = torch.where(terminated, torch.zeros_like(self._elapsed), self._elapsed)
         return team_reward, terminated, {"TimeLimit.truncated": self._truncated, "message": info["message"],
-                                         "remaining": info["remaining"]}
+                                         "remaining": info["remaining"], "fresh": self._fresh}
 
-    def get_obs(self):
-        """List of per-agent observations (one env) or the [B, N, D] tensor."""
+    def fresh_mask(self):
+        """[B] bool: envs whose episode ended at the last step (they begin a new one at the next step)."""
+        return self._fresh
+
+    def get_obs(self, episode_start=False):
+        """List of per-agent observations (one env) or the [B, N, D] tensor.  After a step the rows of finished
+        envs are their terminal observations; episode_start=True returns them zeroed instead (the reference's
+        reset() returns an all-zero observation, e.g. PredatorCapturePrey.py:136)."""
+        if episode_start and self.num_envs > 1 and self._fresh is not None:
+            return torch.where(self._fresh.view(-1, 1, 1), torch.zeros_like(self._obs), self._obs)
         return self._obs
 
     def get_obs_agent(self, agent_id):
@@ -94,10 +114,10 @@ class GymmaVecEnv(object):
     def get_obs_size(self):
         return self._obs_size
 
-    def get_state(self):
+    def get_state(self, episode_start=False):
         if self.num_envs == 1:
             return np.concatenate(self._obs, axis=0).astype(np.float32)
-        return self._obs.reshape(self.num_envs, self.n_agents * self._obs_size)
+        return self.get_obs(episode_start).reshape(self.num_envs, self.n_agents * self._obs_size)
 
     def get_state_size(self):
         return self.n_agents * self._obs_size
@@ -124,7 +144,8 @@ class GymmaVecEnv(object):
             self._obs = self._pad(obs)
         else:
             self._elapsed = torch.zeros((self.num_envs,), dtype=torch.int32, device=obs.device)
-            self._obs = self._pad(obs)
+            self._obs = self._pad(obs).clone()
+            self._fresh = torch.ones((self.num_envs,), dtype=torch.bool, device=obs.device)
         return self.get_obs(), self.get_state()
 
     def render(self):

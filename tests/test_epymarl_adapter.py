@@ -15,6 +15,7 @@ class _FakeScenario(object):
 
     def reset(self, mask=None, seed=None):
         self.reset_masks.append(mask.clone())
+        self.outer.obs_buf[mask] = 0            # like reset_kernel: the re-sampled envs' rows of the obs buffer are zeroed
 
 
 class _FakeWrapper(object):
@@ -25,12 +26,14 @@ class _FakeWrapper(object):
         self.action_space = spaces.Tuple((spaces.Discrete(5), spaces.Discrete(5), spaces.Discrete(3)))
         self.observation_space = spaces.Tuple(tuple(spaces.Box(-1, 1, (w,), np.float32) for w in (4, 6, 4)))
         self.env = _FakeScenario(self)
+        self.obs_buf = torch.zeros((num_envs, 3, 4)) if num_envs > 1 else None      # ONE buffer, rewritten in place
 
     def reset(self):
         self.t = 0
         if self.num_envs == 1:
             return [[0] * 4] * 3
-        return torch.zeros((self.num_envs, 3, 4))
+        self.obs_buf.zero_()
+        return self.obs_buf
 
     def step(self, actions):
         self.t += 1
@@ -38,7 +41,7 @@ class _FakeWrapper(object):
             obs = tuple(np.full(4, self.t + i, dtype=np.float32) for i in range(3))
             return obs, [1.0, 2.0, 3.5], [self.t == self.done_at] * 3, {}
         B = self.num_envs
-        obs = torch.full((B, 3, 4), float(self.t))
+        obs = self.obs_buf.fill_(float(self.t))
         rew = torch.tensor([[1.0, 2.0, 3.5]]).repeat(B, 1)
         done = (torch.arange(B) == self.done_at).unsqueeze(1).expand(B, 3) & (self.t == 2)
         return obs, rew, done, {"message": torch.zeros(B, dtype=torch.uint8), "remaining": torch.zeros(B, dtype=torch.int32)}
@@ -73,6 +76,8 @@ def test_batched_time_limit_and_reset_mask():
     r, term, info = env.step(a)                               # env 1 finishes on its own at t = 2
     assert term.tolist() == [False, True, False, False] and not info["TimeLimit.truncated"].any()
     assert env._elapsed.tolist() == [2, 0, 2, 2]
+    assert info["fresh"].tolist() == [False, True, False, False]
+    assert env.get_obs()[1, 0, 0] == 2.0 and env.get_obs(episode_start=True)[1, 0, 0] == 0.0
     r, term, info = env.step(a)                               # the others hit the limit at t = 3
     assert term.tolist() == [True, False, True, True]
     assert info["TimeLimit.truncated"].tolist() == [True, False, True, True]
@@ -80,6 +85,13 @@ def test_batched_time_limit_and_reset_mask():
     assert env._elapsed.tolist() == [0, 1, 0, 0]
     assert torch.equal(env.get_state(), env.get_obs().reshape(B, -1))
     assert float(env.get_obs()[..., 4:].abs().max()) == 0.0   # zero padding of the short observations
+    # episode boundaries: the terminal observation (t = 3) of the truncated envs survives the masked reset that zeroed
+    # their rows of the env's own buffer, and the own-done env (reset inside the step at t = 2) reports the same way
+    assert float(env._wrapper.obs_buf[0].abs().max()) == 0.0
+    assert env.get_obs()[:, 0, 0].tolist() == [3.0, 3.0, 3.0, 3.0]
+    assert info["fresh"].tolist() == [True, False, True, True] and torch.equal(env.fresh_mask(), info["fresh"])
+    assert env.get_obs(episode_start=True)[:, 0, 0].tolist() == [0.0, 3.0, 0.0, 0.0]
+    assert env.get_state(episode_start=True)[:, 0].tolist() == [0.0, 3.0, 0.0, 0.0]
 
 
 @pytest.mark.gpu
@@ -96,6 +108,12 @@ def test_adapter_on_the_cuda_env():
         assert torch.allclose(r, env._env.vec.reward.sum(dim=1))
         ended |= term
     assert bool(term.any()) and bool(ended.all())             # everybody is cut at the limit at the latest
+    # truncated envs were re-sampled by mrb_reset (their rows of the device obs buffer are zero now); the adapter still
+    # reports their terminal observations, and zeros as the first observation of the next episode
+    trunc = info["TimeLimit.truncated"]
+    assert bool(trunc.any()) and float(env._env.vec.obs[trunc].abs().max()) == 0.0
+    assert bool((env.get_obs()[trunc].abs().amax(dim=(1, 2)) > 0).all())
+    assert float(env.get_obs(episode_start=True)[term].abs().max()) == 0.0
     single = GymmaVecEnv("robotarium_gym:MaterialTransport-v0", time_limit=4, seed=1)
     obs, state = single.reset()
     assert len(obs) == 4 and state.shape == (36,)
