@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--override", action="append", default=[], help="config key=value (python literal)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to the CPUs next to its GPU")
     ap.add_argument("--rollout", action="store_true",
                     help="also time the closed loop policy kernel -> step kernel (SURVEY 8f-1), random-init GRU agent")
     return ap.parse_args()
@@ -61,16 +62,23 @@ def workload_name(args, cfg, world):
         args.scenario, args.envs, world, cfg.get("barrier_certificate", "safe"))
 
 
-def algorithmic_bytes_per_env_step(env):
-    """HBM bytes one env step must move with this layout: state rows read and
-    written once, actions in, obs / reward / done / message / remaining / dist out."""
+def layout_bytes_per_env_step(env):
+    """HBM bytes one env step moves with THIS layout: state rows read and written once, actions
+    in, obs / reward / done / message / remaining / dist out - SURVEY 8(d)'s figure plus the rows it calls optional
+    (previous pose, dist_travelled, episode return, episode counter)."""
     N, D = env.N, env.D
     rf, ri = env.state_f64.shape[0], env.state_i32.shape[0]
-    scen_f = rf - (5 * N + 1)
     read = 8 * rf + 4 * ri + 4 * N
     write = 8 * (5 * N + 1) + 4 * ri + 4 * N * D + 4 * N + 1 + 1 + 4 + (4 * N if env.dist is not None else 0)
-    del scen_f
     return read + write
+
+
+def algorithmic_bytes_per_env_step(scenario, N, D, P):
+    """48N (pose r+w) + 4N (actions) + 4*N*D (obs) + rewards + 2 (done, message) + scenario state.
+    PCP 582, Warehouse 782, MaterialTransport 422, ArcticTransport 818, Simple 410, PCP-20 2,438 B."""
+    base = 48 * N + 4 * N + 4 * N * D + 2
+    return base + {"PredatorCapturePrey": 4 + 16 * P + 16, "Warehouse": 4 * N + 12, "MaterialTransport": 4 + 64,
+                   "ArcticTransport": 4 + 96 + 28, "Simple": 4 * N + 16 + 8}[scenario]
 
 
 class ClockSampler(threading.Thread):
@@ -218,23 +226,27 @@ def time_rollout(env, steps):
             "policy": "RNNAgent hidden 128, GRUCell, obs_agent_id, greedy; persistent tcgen05 / TMEM kernel, FP16 operands, FP32 accumulate; random-init weights"}
 
 
-def fp64_pipe_from_profile(scenario, B):
-    """FP64-pipe utilisation of the step kernel from the committed ncu capture of this workload (a profiler number,
-    quoted beside the live timing, never measured under it): the roofline that binds."""
-    name = {("PredatorCapturePrey", 65536): "r01_ncu_step_thread_pcp4_final_raw.csv",
-            ("Warehouse", 262144): "r01_ncu_step_thread_wh6_cta256_raw.csv"}.get((scenario, B))
-    if name is None:
-        return {}
-    path = os.path.join(ROOT, "profiles", name)
-    try:
-        import csv
-        rows = list(csv.reader(open(path)))
-        d = dict(zip(rows[0], rows[2]))
-        return {"pipe_pct_of_peak": float(d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]),
-                "issue_slots_pct": float(d["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]),
-                "pipe_source": "profiles/" + name}
-    except Exception:
-        return {}
+def pcie_floor(env, world, barrier, reps=10):
+    """Bare pinned device->host copy of one step's outputs, all ranks at once: the floor of the e2e path."""
+    import torch
+    n = env.d2h_bytes_per_step
+    src = torch.empty(n, dtype=torch.uint8, device=env.device)
+    dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=env.device)
+    if world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    per = float(dt.item()) / reps
+    return {"d2h_ms_per_step": per * 1e3, "aggregate_gbs": world * n / per / 1e9, "bytes_per_gpu": n,
+            "env_steps_per_s_at_floor": world * env.B / per,
+            "how": "every rank copies one step's outputs (obs + reward + done + message) device -> pinned host, "
+                   "%d times back to back, all ranks at once; max over ranks" % reps}
 
 
 def run_ours(args):
@@ -242,14 +254,21 @@ def run_ours(args):
     import torch
     from marbler_b200 import build, sharding
     from marbler_b200.vec_env import VecEnv
+    from marbler_b200 import flop_model
+    from marbler_b200.vec_env import fp64_peak
     build.build()
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # run on the CPUs next to this rank's GPU BEFORE anything allocates pinned memory (first touch decides the NUMA
+    # node of the host buffers the e2e path copies into); the full mask is restored for the CPU baseline leg
+    all_cpus = os.sched_getaffinity(0)
+    numa = sharding.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0"))) if not args.no_numa_bind else None
     rank, world, local = sharding.init_distributed()
     if world == 1 and args.gpus > 1:
         raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    fp64_tflops = fp64_peak(local, 150.0)       # measured DFMA rate of this GPU: the denominator of the binding roofline
     cfg = load_cfg(args)
     B, K, W = args.envs, args.steps, args.warmup
     env = VecEnv(args.scenario, cfg, num_envs=B, device=dev, seed=0, env_id0=rank * B, auto_reset=True)
@@ -309,6 +328,7 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_rate = world * B * Ke / float(e2e_s.item())
+    floor = pcie_floor(env, world, barrier)
 
     rollout = time_rollout(env, min(K, 320)) if args.rollout else None
     if rank != 0:
@@ -317,7 +337,9 @@ def run_ours(args):
         return
     value = world * B * K / (dev_ms_max * 1e-3)
     ms_per_step = dev_ms_max / K
-    bytes_step = algorithmic_bytes_per_env_step(env)
+    bytes_step = algorithmic_bytes_per_env_step(args.scenario, env.N, env.D, env.P)
+    flops = flop_model.flops(args.scenario, env.N, stats)          # stats: summed over ranks, timed region only
+    fp64_achieved = None if flops is None else flops["total"] / world / (dev_ms_max * 1e-3) / 1e12      # per GPU
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_kind = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, 6.65 TB/s)"
     if os.path.exists(peaks_path):
@@ -346,22 +368,36 @@ def run_ours(args):
         "agent_steps_per_s": value * env.N,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind, "bytes_per_env_step": bytes_step,
-                     "kernel": "step_thread_kernel<%s,%d>" % (args.scenario, env.N),
-                     "note": "the step is FP64-issue bound, not HBM bound (SURVEY 8d, DESIGN.md section 5); "
-                             "fp64 object below is the binding roofline"},
-        "fp64": dict({"ipm_iterations_per_solve": stats["qp_iters_per_solve"],
-                      "qp_solves_per_env_step": stats["qp_solves"] / max(stats["env_steps"], 1.0),
-                      "qp_stalls": stats["qp_stalls"]}, **fp64_pipe_from_profile(args.scenario, B)),
+                     "bytes_layout": layout_bytes_per_env_step(env),
+                     "kernel": "%s<%s,%d>" % ("step_thread_kernel" if env.N <= 6 else "step_warp_kernel", args.scenario, env.N),
+                     "note": "bytes_per_env_step is SURVEY 8(d)'s figure; bytes_layout adds the optional rows this layout "
+                             "keeps.  The step is FP64-issue bound, not HBM bound (SURVEY 8d): roofline_fp64 is the "
+                             "binding roofline"},
+        "roofline_fp64": None if flops is None else {
+            "bound": "fp64", "achieved": fp64_achieved, "peak": fp64_tflops, "unit": "TFLOP/s",
+            "frac": fp64_achieved / fp64_tflops,
+            "flops_per_env_step": flops["total"] / max(stats["env_steps"], 1.0),
+            "peak_kind": "measured in this run: mrb_fp64_peak (independent DFMA chains, best launch)",
+            "model": flops["model"], "per_gpu": True},
+        "fp64": {"ipm_iterations_per_solve": stats["qp_iters_per_solve"],
+                 "qp_solves_per_env_step": stats["qp_solves"] / max(stats["env_steps"], 1.0),
+                 "substeps_per_env_step": stats["substeps"] / max(stats["env_steps"], 1.0),
+                 "qp_stalls": stats["qp_stalls"],
+                 # iterations the warps ran / iterations the envs needed (one env per thread: a warp waits for its
+                 # slowest env): the divergence overhead of the solver loop
+                 "warp_iteration_overhead": stats["qp_iterations_warp"] / max(stats["qp_iterations"], 1.0)},
         "episodes": {k: stats[k] for k in ("episodes", "return_mean", "length_mean", "collisions", "boundary_exits", "timeouts")},
         "clocks": clocks,
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                 "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": Ke,
-                "api": "VecEnv.step_host -> mrb_step_host (pinned host buffers, one sync per step)"},
+                "api": "VecEnv.step_host -> mrb_step_host (pinned host buffers, one sync per step)",
+                "pcie_floor": floor, "cpu_affinity": numa},
         "gpu_launches": int(launches),
     }
     if args.rollout:
         out["rollout"] = rollout
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)       # the CPU leg gets every host core back
         out["cpu_baseline"], _, _, _ = cpu_port_rate(args, cfg, args.cpu_seconds)
     print(json.dumps(out))
     if world > 1:

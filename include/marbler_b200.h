@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define MRB_ABI_VERSION 1
+#define MRB_ABI_VERSION 2
 #define MRB_MAX_ROBOTS 32
 #define MRB_MAX_PREY 32
 
@@ -39,7 +39,7 @@ typedef struct mrb_spawn {
 typedef struct mrb_config {
     int32_t struct_size;            /* sizeof(mrb_config), checked by mrb_create */
     int32_t scenario;               /* MRB_PCP ... */
-    int32_t num_robots;             /* PCP: predator+capture (PredatorCapturePrey.py:19); else n_agents */
+    int32_t num_robots;             /* PCP: predator+capture (PredatorCapturePrey.py:19); else n_agents; 2..32 */
     int32_t update_frequency;       /* roboEnv.py:52 */
     int32_t ctrl_period;            /* 15, roboEnv.py:63 */
     int32_t robotarium;             /* roboEnv.py:63: controller every sub-step */
@@ -66,6 +66,12 @@ typedef struct mrb_config {
     double violation_reward;        /* -5 / -5 / -6 / -30 / -5 (literals in each scenario's step()) */
     double zone_mu[2], zone_sigma[2];                /* MaterialTransport zone1/zone2 normal(loc, scale) */
     mrb_spawn spawn_robots, spawn_other;             /* robots; PCP prey / Simple goal */
+    /* rps RobotariumABC._validate collision test (roboEnv.py:80-94 reads its counters): a pair collides when
+     * |(p_j + collision_offset (cos th_j, sin th_j)) - (p_k + collision_offset (cos th_k, sin th_k))| <= collision_diameter.
+     * rps is not vendored in the reference and its pinned commit (6bb184e) cannot be read in the build container,
+     * so both published forms are supported: centre to centre (collision_offset = 0; the SURVEY.md App. A.4
+     * restatement, the default of the Python layer) and heading-projected points (collision_offset = 0.025). */
+    double collision_diameter, collision_offset;
 } mrb_config;
 
 /* Caller-owned device buffers.  State is structure-of-arrays with the env index fastest:
@@ -77,7 +83,12 @@ typedef struct mrb_config {
 enum { MRB_STAT_EPISODES = 0, MRB_STAT_RETURN = 1, MRB_STAT_LENGTH = 2, MRB_STAT_COLLISION = 3,
        MRB_STAT_BOUNDARY = 4, MRB_STAT_SCENARIO = 5, MRB_STAT_ENV_STEPS = 6, MRB_STAT_QP_SOLVES = 7,
        MRB_STAT_QP_ITERS = 8, MRB_STAT_TIMEOUTS = 9,
-       MRB_STAT_QP_STALLS = 10 /* solves that ran >= 25 iterations: cvxopt's iteration caught in a limit cycle */ };
+       MRB_STAT_QP_STALLS = 10, /* solves that ran >= 25 iterations: cvxopt's iteration caught in a limit cycle */
+       MRB_STAT_SUBSTEPS = 11,  /* simulator sub-steps executed (update_frequency per env step unless a violation ends it early) */
+       /* iterations the hardware ran for the solves: with one env per thread a warp iterates until its slowest
+        * env has converged, so this is the sum over solves of (warp maximum x lanes of the warp); divided by
+        * MRB_STAT_QP_ITERS it is the divergence overhead of the solver loop (1.0 for the one-env-per-warp kernels) */
+       MRB_STAT_QP_ITERS_WARP = 12 };
 typedef struct mrb_buffers {
     double *state_f64;
     int32_t *state_i32;
@@ -88,6 +99,11 @@ typedef struct mrb_buffers {
     int32_t *remaining;
     float *dist;
     double *stats;
+    /* optional float64 copies of obs / reward (NULL = off).  The reference returns float64 numpy observations and
+     * Python-float rewards (e.g. PredatorCapturePrey.py:176); the single-env drop-in path binds these so that its
+     * return values are not rounded through float32. */
+    double *obs_f64;    /* [B][N][D] */
+    double *reward_f64; /* [B][N] */
 } mrb_buffers;
 
 typedef struct mrb_env mrb_env;
@@ -122,6 +138,36 @@ int mrb_step(mrb_env *env, const int32_t *actions, void *cuda_stream);
  * buffers bound with mrb_bind are written in every mode. */
 int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *obs_host, float *reward_host,
                   uint8_t *done_host, uint8_t *message_host, void *cuda_stream);
+/* ---- state access by field (checkpoint / restore, parity injection).  The reference keeps this state in Python
+ * attributes of the scenario, its agents and roboEnv (cited per field); here it is packed into the SoA rows of
+ * state_f64 / state_i32, and these two calls convert between the rows and plain per-field HOST arrays for the envs
+ * [env_lo, env_lo + count).  NULL fields are skipped (get) / left unchanged (set); fields of other scenarios are
+ * ignored.  Both calls are ordered after the work already enqueued on cuda_stream and synchronise before returning. */
+typedef struct mrb_state_fields {
+    int32_t struct_size;         /* sizeof(mrb_state_fields) */
+    int32_t reserved0;
+    double *poses;               /* [count][3][N]  scenario.agent_poses = robotarium.poses (x row, y row, theta row) */
+    double *prev_pose;           /* [count][3][N]  roboEnv.previous_pose (roboEnv.py:55-59); only x, y are state, theta reads 0 */
+    double *episode_return;      /* [count]        sum of team rewards of the running episode (statistics only) */
+    int32_t *episode_steps;      /* [count]        scenario.episode_steps */
+    int32_t *prev_valid;         /* [count]        roboEnv.previous_pose is not None (roboEnv.py:117) */
+    int32_t *episode_count;      /* [count]        episodes started so far: Philox counter of the next auto-reset */
+    double *prey_loc;            /* [count][P][2]  PCP prey_loc (PredatorCapturePrey.py:128-132) */
+    uint8_t *prey_sensed;        /* [count][P]     PCP prey_sensed */
+    uint8_t *prey_captured;      /* [count][P]     PCP prey_captured */
+    uint8_t *loaded;             /* [count][N]     Warehouse agent.loaded (warehouse.py:145-178) */
+    int32_t *load;               /* [count][N]     MaterialTransport agent.load */
+    int32_t *zone_load;          /* [count][2]     MaterialTransport zone1_load, zone2_load (MaterialTransport.py:99-100) */
+    int32_t *messages;           /* [count][4]     MaterialTransport messages (MaterialTransport.py:119-120) */
+    uint8_t *grid;               /* [count][8][12] ArcticTransport grid (ArcticTransport.py:56-82) */
+    int32_t *goal_col;           /* [count]        ArcticTransport goal_loc[1] */
+    int32_t *pixel_type;         /* [count][N]     ArcticTransport agent.pixel_type (agent.py:37-39) */
+    uint8_t *reached_goal;       /* [count][N]     ArcticTransport agent.reached_goal */
+    double *goal;                /* [count][2]     Simple goal_loc (simple.py:141-144) */
+} mrb_state_fields;
+int mrb_get_state(mrb_env *env, int64_t env_lo, int64_t count, const mrb_state_fields *out, void *cuda_stream);
+int mrb_set_state(mrb_env *env, int64_t env_lo, int64_t count, const mrb_state_fields *in, void *cuda_stream);
+
 /* unit entry for the barrier-certificate QP alone (rps create_single_integrator_barrier_certificate{,2}
  * -> cvxopt.solvers.qp; called at controller.py:23).  Device SoA: dxi, xi, u are f64 [2][N][B];
  * iters i32 [B] (may be NULL). */
@@ -161,6 +207,12 @@ const char *mrb_policy_last_error(const mrb_policy *policy);
  * All device pointers; stream-ordered, no synchronisation. */
 int mrb_policy_act(mrb_policy *policy, int64_t num_envs, const float *obs, float *hidden, int32_t *actions,
                    float *q, const uint8_t *fresh, void *cuda_stream);
+
+/* FP64 roofline denominator, measured: runs a kernel of independent DFMA chains (16 per thread, 148 x 8 CTAs of
+ * 256 threads) for about `milliseconds` on `device`, timed with CUDA events, and returns the sustained rate in
+ * TFLOP/s (2 flops per DFMA).  The env step is bound by FP64 issue, not by HBM, so bench.py
+ * reports the step kernels' FP64 flop rate against this number. */
+int mrb_fp64_peak(int device, double milliseconds, double *tflops);
 
 /* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
 int64_t mrb_launch_count(void);

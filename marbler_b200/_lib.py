@@ -5,13 +5,13 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MARBLER_B200_LIB") or os.path.join(HERE, "libmarbler_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 NUM_STATS = 16
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "collisions", "boundary_exits", "scenario_metric",
-              "env_steps", "qp_solves", "qp_iterations", "timeouts", "qp_stalls")
+              "env_steps", "qp_solves", "qp_iterations", "timeouts", "qp_stalls", "substeps", "qp_iterations_warp")
 SYMBOLS = ("mrb_version", "mrb_create", "mrb_destroy", "mrb_last_error", "mrb_state_rows", "mrb_obs_dim",
            "mrb_num_actions", "mrb_bind", "mrb_reset", "mrb_step", "mrb_step_host", "mrb_barrier_qp",
-           "mrb_launch_count", "mrb_policy_create", "mrb_policy_destroy", "mrb_policy_last_error", "mrb_policy_act")
+           "mrb_get_state", "mrb_set_state", "mrb_fp64_peak", "mrb_launch_count", "mrb_policy_create", "mrb_policy_destroy", "mrb_policy_last_error", "mrb_policy_act")
 
 
 class Spawn(C.Structure):
@@ -32,12 +32,34 @@ class Config(C.Structure):
             "goal_width", "zone1_radius", "not_reached_penalty", "dist_multiplier", "reward_scaler",
             "violation_reward")] + \
         [("zone_mu", C.c_double * 2), ("zone_sigma", C.c_double * 2),
-         ("spawn_robots", Spawn), ("spawn_other", Spawn)]
+         ("spawn_robots", Spawn), ("spawn_other", Spawn),
+         ("collision_diameter", C.c_double), ("collision_offset", C.c_double)]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state_f64", "state_i32", "obs", "reward", "done", "message",
-                                          "remaining", "dist", "stats")]
+                                          "remaining", "dist", "stats", "obs_f64", "reward_f64")]
+
+
+# mrb_state_fields: (name, numpy dtype, shape per env as a function of (N, P)); order = the C struct
+STATE_FIELDS = (
+    ("poses", "f8", lambda N, P: (3, N)), ("prev_pose", "f8", lambda N, P: (3, N)), ("episode_return", "f8", lambda N, P: ()),
+    ("episode_steps", "i4", lambda N, P: ()), ("prev_valid", "i4", lambda N, P: ()), ("episode_count", "i4", lambda N, P: ()),
+    ("prey_loc", "f8", lambda N, P: (P, 2)), ("prey_sensed", "u1", lambda N, P: (P,)), ("prey_captured", "u1", lambda N, P: (P,)),
+    ("loaded", "u1", lambda N, P: (N,)),
+    ("load", "i4", lambda N, P: (N,)), ("zone_load", "i4", lambda N, P: (2,)), ("messages", "i4", lambda N, P: (4,)),
+    ("grid", "u1", lambda N, P: (8, 12)), ("goal_col", "i4", lambda N, P: ()), ("pixel_type", "i4", lambda N, P: (N,)),
+    ("reached_goal", "u1", lambda N, P: (N,)),
+    ("goal", "f8", lambda N, P: (2,)),
+)
+COMMON_FIELDS = ("poses", "prev_pose", "episode_return", "episode_steps", "prev_valid", "episode_count")
+SCENARIO_FIELDS = {"PredatorCapturePrey": ("prey_loc", "prey_sensed", "prey_captured"), "Warehouse": ("loaded",),
+                   "MaterialTransport": ("load", "zone_load", "messages"),
+                   "ArcticTransport": ("grid", "goal_col", "pixel_type", "reached_goal"), "Simple": ("goal",)}
+
+
+class StateFields(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("reserved0", C.c_int32)] + [(n, C.c_void_p) for n, _, _ in STATE_FIELDS]
 
 
 class PolicyDesc(C.Structure):
@@ -71,6 +93,9 @@ def load():
         "mrb_step": ([vp, vp, vp], C.c_int),
         "mrb_step_host": ([vp, vp, vp, vp, vp, vp, vp], C.c_int),
         "mrb_barrier_qp": ([C.c_int, i32, i32, i64, vp, vp, vp, vp, vp], C.c_int),
+        "mrb_get_state": ([vp, i64, i64, C.POINTER(StateFields), vp], C.c_int),
+        "mrb_set_state": ([vp, i64, i64, C.POINTER(StateFields), vp], C.c_int),
+        "mrb_fp64_peak": ([C.c_int, C.c_double, C.POINTER(C.c_double)], C.c_int),
         "mrb_launch_count": ([], i64),
         "mrb_policy_create": ([C.POINTER(PolicyDesc), C.c_int, vp, i64, C.POINTER(vp)], C.c_int),
         "mrb_policy_destroy": ([vp], C.c_int),

@@ -10,6 +10,10 @@ from . import _lib
 SCENARIOS = ("PredatorCapturePrey", "Warehouse", "MaterialTransport", "ArcticTransport", "Simple")
 GYM_KEYS = {s: s + "-v0" for s in SCENARIOS}                      # robotarium_gym/__init__.py:4-10
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
+# defaults of the two rps collision constants (overridable per config with rps_collision_diameter / rps_collision_offset,
+# or for a whole process with the environment variables below)
+RPS_COLLISION_DIAMETER = float(os.environ.get("MRB_RPS_COLLISION_DIAMETER", "0.135"))
+RPS_COLLISION_OFFSET = float(os.environ.get("MRB_RPS_COLLISION_OFFSET", "0.0"))
 
 
 class objectview(object):
@@ -60,6 +64,11 @@ def make_config(scenario, cfg, auto_reset=False, track_dist=True, collect_stats=
     c.capability_aware = int(bool(g("capability_aware", False)))
     c.auto_reset, c.track_dist, c.collect_stats = int(auto_reset), int(track_dist), int(collect_stats)
     c.left, c.right, c.up, c.down = cfg["LEFT"], cfg["RIGHT"], cfg["UP"], cfg["DOWN"]
+    # rps RobotariumABC._validate's collision test (not a key of the reference's config.yaml: rps hard-codes it).
+    # rps is un-vendored and its pinned commit cannot be read here, so both published forms are selectable:
+    # centre to centre (offset 0, the restatement every fixture was made with) or heading-projected points (0.025)
+    c.collision_diameter = float(g("rps_collision_diameter", RPS_COLLISION_DIAMETER))
+    c.collision_offset = float(g("rps_collision_offset", RPS_COLLISION_OFFSET))
     height = cfg["DOWN"] - cfg["UP"]
     if scenario == "PredatorCapturePrey":
         c.num_robots = cfg["predator"] + cfg["capture"]

@@ -9,36 +9,25 @@
 #include <string>
 
 #include "common.cuh"
+#include "handle.h"
 #include "launchers.h"
 
 using namespace mrb;
 
-constexpr int kPipeStreams = 16;
-
-struct mrb_env {
-    Params p;
-    int device;
-    bool bound;
-    int32_t *actions_dev;       // staging for mrb_step_host
-    cudaStream_t pipe[kPipeStreams];   // internal streams of the chunked host path (one per chunk)
-    cudaEvent_t ev_in, ev_out[kPipeStreams];
-    bool pipe_ready;
-    std::string err;
-};
-
 static std::string g_create_error;
 static std::atomic<int64_t> g_launches{0};
-namespace mrb { void count_launch() { g_launches++; } }
-
-static int fail(mrb_env *e, int code, const std::string &msg)
+namespace mrb {
+void count_launch() { g_launches++; }
+int fail(mrb_env *e, int code, const std::string &msg)
 {
     if (e) e->err = msg; else g_create_error = msg;
     return code;
 }
-static int cuda_fail(mrb_env *e, cudaError_t st, const char *what)
+int cuda_fail(mrb_env *e, cudaError_t st, const char *what)
 {
     return fail(e, MRB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(st));
 }
+}  // namespace mrb
 
 // largest t with fl(sqrt(t)) <= r: sqrt(d2) <= r  <=>  d2 <= t for every double d2 >= 0
 static double thr2(double r)
@@ -78,7 +67,10 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
         return fail(nullptr, MRB_E_ARG, "mrb_create: mrb_config.struct_size does not match this library (ABI mismatch)");
     const mrb_config &c = *cfg;
     if (c.scenario < MRB_PCP || c.scenario > MRB_SIMPLE) return fail(nullptr, MRB_E_ARG, "mrb_create: unknown scenario");
-    if (c.num_robots < 1 || c.num_robots > MRB_MAX_ROBOTS) return fail(nullptr, MRB_E_ARG, "mrb_create: num_robots must be in [1, 32]");
+    // one robot has no pair constraint: rps' certificate would hand cvxopt an empty G, which the reference never does
+    if (c.num_robots < 2 || c.num_robots > MRB_MAX_ROBOTS) return fail(nullptr, MRB_E_ARG, "mrb_create: num_robots must be in [2, 32]");
+    if (!(c.collision_diameter > 0.0) || !(c.collision_offset >= 0.0) || !std::isfinite(c.collision_diameter + c.collision_offset))
+        return fail(nullptr, MRB_E_ARG, "mrb_create: collision_diameter must be > 0 and collision_offset >= 0 (rps: 0.135 and 0 or 0.025)");
     if (num_envs < 1) return fail(nullptr, MRB_E_ARG, "mrb_create: num_envs must be >= 1");
     if (c.update_frequency < 1 || c.ctrl_period < 1) return fail(nullptr, MRB_E_ARG, "mrb_create: update_frequency / ctrl_period must be >= 1");
     if (c.scenario == MRB_PCP && (c.num_prey < 1 || c.num_prey > MRB_MAX_PREY || c.num_predators < 0 || c.num_predators > c.num_robots))
@@ -123,7 +115,7 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
     e->p.obs_blocks = obs_block_count(c);
     e->p.rows_f64 = rows_f64(c);
     e->p.rows_i32 = rows_i32(c);
-    e->p.collision_thr2 = thr2(kCollisionDiameter);
+    e->p.collision_thr2 = thr2(c.collision_diameter);
     e->p.sense_thr2 = thr2(c.predator_radius);
     e->p.capture_thr2 = thr2(c.capture_radius);
     e->p.zone1_thr2 = thr2(c.zone1_radius);

@@ -12,7 +12,6 @@ namespace mrb {
 constexpr double kTimeStep = 0.033;
 constexpr double kMaxLinearVelocity = 0.2;
 constexpr double kMaxAngularVelocity = 2.0 * (0.016 / 0.11) * (0.2 / 0.016);
-constexpr double kCollisionDiameter = 0.135;
 constexpr double kArenaXMin = -1.6, kArenaXMax = -1.6 + 3.2, kArenaYMin = -1.0, kArenaYMax = -1.0 + 2.0;
 // controller constants (App. A.6 - A.8)
 constexpr double kProjectionDistance = 0.05;

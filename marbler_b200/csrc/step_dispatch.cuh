@@ -26,7 +26,8 @@ inline cudaError_t launch_step_generic(const Params &p, const int32_t *actions, 
 {
     *launched = true;
     static const bool force_warp = std::getenv("MRB_FORCE_WARP") != nullptr;      // measurement aid
-    if (!force_warp) switch (p.cfg.num_robots) {
+    // (ignored for ArcticTransport, which only exists on the thread kernel)
+    if (!force_warp || SCN == MRB_ARCTIC) switch (p.cfg.num_robots) {
     case 2: if (SCN != MRB_MATERIAL) return launch_thread<SCN, (SCN != MRB_MATERIAL ? 2 : 4)>(p, actions, s); break;
     case 3: if (SCN != MRB_MATERIAL) return launch_thread<SCN, (SCN != MRB_MATERIAL ? 3 : 4)>(p, actions, s); break;
     case 4: return launch_thread<SCN, 4>(p, actions, s);
@@ -34,6 +35,7 @@ inline cudaError_t launch_step_generic(const Params &p, const int32_t *actions, 
     case 6: return launch_thread<SCN, 6>(p, actions, s);
     default: break;
     }
+    if (SCN == MRB_ARCTIC) { *launched = false; return cudaSuccess; }
     return launch_step_warp<SCN>(p, actions, s);
 }
 

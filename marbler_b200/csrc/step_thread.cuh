@@ -146,6 +146,18 @@ __device__ __forceinline__ int arctic_grid(const uint32_t (&g)[6], int row, int 
     return (w >> (2 * (k & 15))) & 3;
 }
 
+// one agent's observation row: float32 always, plus the optional float64 copy (mrb_buffers.obs_f64)
+struct ObsRow {
+    float *f;
+    double *d;
+    __device__ __forceinline__ ObsRow(float *f_, double *d64, int64_t off) : f(f_ + off), d(d64 ? d64 + off : nullptr) {}
+    __device__ __forceinline__ void put(int k, double v) const
+    {
+        f[k] = (float)v;
+        if (d) d[k] = v;
+    }
+};
+
 // ---- reset: <Scenario>.reset() + roboEnv.reset() (distributional parity)
 // N distinct cells of the spawn grid, uniformly, in order (rps generate_initial_conditions, App. A.5)
 template <typename F>
@@ -237,6 +249,8 @@ __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *ma
     const int nd = p.cfg.num_robots * p.obs_dim;
     float *o = p.buf.obs + env * nd;
     for (int k = 0; k < nd; k++) o[k] = 0.f;
+    if (p.buf.obs_f64)
+        for (int k = 0; k < nd; k++) p.buf.obs_f64[env * nd + k] = 0.0;
 }
 
 // ---- the step
@@ -295,9 +309,11 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             dist[i] = sqrt(dx * dx + dy * dy);
         }
     }
-    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0;
+    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_itw = 0, n_sub = 0;
     const int UF = c.update_frequency;
+    const double coff = c.collision_offset;
     for (int k = 0; k < UF; k++) {                // roboEnv.py:52
+        n_sub++;
         // :55-56 for k >= 1: |pose_k - pose_{k-1}| = dt |v_{k-1}| (c^2 + s^2 = 1)
         if (k > 0) {
 #pragma unroll
@@ -324,6 +340,10 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             n_it += it;
             n_stall += it >= 25;
             n_qp++;
+            if (c.collect_stats) {                 // the warp iterated until its slowest env converged
+                const unsigned here = __activemask();
+                n_itw += __reduce_max_sync(here, it);
+            }
 #pragma unroll
             for (int i = 0; i < N; i++) {                                   // si_to_uni_dyn (A.7) + saturation (A.2)
                 double vv = cs[i] * ux[i] + sn[i] * uy[i];
@@ -339,13 +359,20 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
 #pragma unroll
         for (int i = 0; i < N; i++)
             viol_b |= (px[i] < kArenaXMin) | (px[i] > kArenaXMax) | (py[i] < kArenaYMin) | (py[i] > kArenaYMax);
+        {
+            // collision points: the centres, or (collision_offset != 0) the points projected along the heading;
+            // (cs, sn) is the heading of the entering pose here (fresh at k = 0, advanced with the pose since)
+            double cxp[N], cyp[N];
 #pragma unroll
-        for (int i = 0; i < N - 1; i++)
+            for (int i = 0; i < N; i++) { cxp[i] = fma(coff, cs[i], px[i]); cyp[i] = fma(coff, sn[i], py[i]); }
 #pragma unroll
-            for (int j = i + 1; j < N; j++) {
-                const double dx = px[i] - px[j], dy = py[i] - py[j];
-                viol_c |= (dx * dx + dy * dy) <= p.collision_thr2;
-            }
+            for (int i = 0; i < N - 1; i++)
+#pragma unroll
+                for (int j = i + 1; j < N; j++) {
+                    const double dx = cxp[i] - cxp[j], dy = cyp[i] - cyp[j];
+                    viol_c |= (dx * dx + dy * dy) <= p.collision_thr2;
+                }
+        }
 #pragma unroll
         for (int i = 0; i < N; i++) {
             px[i] = px[i] + kTimeStep * cs[i] * v[i];
@@ -369,6 +396,8 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     // ---------------------------------------------------------------- scenario tail (order matters)
     const int D = p.obs_dim;
     float *obs = p.buf.obs + env * (int64_t)(N * D);
+    double *obs64 = p.buf.obs_f64 ? p.buf.obs_f64 + env * (int64_t)(N * D) : nullptr;
+    double *rew64 = p.buf.reward_f64 ? p.buf.reward_f64 + env * N : nullptr;
     float rew[N];
     bool done = false;
     int remaining = 0, scen_metric = 0;
@@ -397,11 +426,16 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             }
             if (sense) sensed |= 1u << q;
             if (((sensed >> q) & 1) && capture) { captured |= 1u << q; continue; }
-            // Agent.get_observation (agent.py:19-46): closest uncaptured prey inside own sensing radius
+            // Agent.get_observation (agent.py:19-46): closest uncaptured prey inside own sensing radius.  The
+            // reference compares the ROUNDED norms (utilities/misc.py:14-18 is_close) with a strict `<`, so two prey
+            // whose squared distances differ by an ulp but round to the same norm keep the first one
 #pragma unroll
             for (int a = 0; a < N; a++) {
                 const bool in_range = d2[a] <= (a < c.num_predators ? p.sense_thr2 : 0.0);
-                if (in_range && (bd[a] < 0.0 || d2[a] < bd[a])) { bd[a] = d2[a]; bx[a] = qxp; by[a] = qyp; }
+                if (in_range) {
+                    const double dd = neighbor_dist(px[a] - qxp, py[a] - qyp);
+                    if (bd[a] < 0.0 || dd < bd[a]) { bd[a] = dd; bx[a] = qxp; by[a] = qyp; }
+                }
             }
         }
         const int unseen = P - __popc(sensed), left = P - __popc(captured);
@@ -412,11 +446,11 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         for (int a = 0; a < N; a++) {
             int slot = 0;
             auto put = [&](int b) {
-                float *o = obs + a * D + slot * od;
-                o[0] = (float)px[b]; o[1] = (float)py[b]; o[2] = (float)bx[b]; o[3] = (float)by[b];
+                const ObsRow o(obs, obs64, a * D + slot * od);
+                o.put(0, px[b]); o.put(1, py[b]); o.put(2, bx[b]); o.put(3, by[b]);
                 if (od == 6) {
-                    o[4] = (float)(b < c.num_predators ? c.predator_radius : 0.0);
-                    o[5] = (float)(b < c.num_predators ? 0.0 : c.capture_radius);
+                    o.put(4, b < c.num_predators ? c.predator_radius : 0.0);
+                    o.put(5, b < c.num_predators ? 0.0 : c.capture_radius);
                 }
                 slot++;
             };
@@ -439,14 +473,14 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                 }
             }
         }
-        float r;
-        if (msg) { r = (float)c.violation_reward; done = true; }           // PredatorCapturePrey.py:155-159
+        double r;
+        if (msg) { r = c.violation_reward; done = true; }                  // PredatorCapturePrey.py:155-159
         else {                                                             // get_rewards (:209-216)
-            r = (float)(((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty);
+            r = ((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty;
             done = steps > c.max_episode_steps || left == 0;
         }
 #pragma unroll
-        for (int a = 0; a < N; a++) rew[a] = r;
+        for (int a = 0; a < N; a++) { rew[a] = (float)r; if (rew64) rew64[a] = r; }
         remaining = left; scen_metric = P - left;
     } else if (SCN == MRB_WAREHOUSE) {
         uint32_t loaded = (uint32_t)sci[0];
@@ -454,8 +488,8 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         for (int a = 0; a < N; a++) {                                       // get_observations (warehouse.py:124-143)
             int slot = 0;
             auto put = [&](int b) {
-                float *o = obs + a * D + slot * 3;
-                o[0] = (float)px[b]; o[1] = (float)py[b]; o[2] = (float)((loaded >> b) & 1);
+                const ObsRow o(obs, obs64, a * D + slot * 3);
+                o.put(0, px[b]); o.put(1, py[b]); o.put(2, (double)((loaded >> b) & 1));
                 slot++;
             };
             put(a);
@@ -479,7 +513,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         }
         if (msg) {
 #pragma unroll
-            for (int a = 0; a < N; a++) rew[a] = (float)c.violation_reward;
+            for (int a = 0; a < N; a++) { rew[a] = (float)c.violation_reward; if (rew64) rew64[a] = c.violation_reward; }
             done = true;
         } else {                                                            // get_rewards (:145-178)
 #pragma unroll
@@ -496,6 +530,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                     }
                 }
                 rew[a] = (float)r;
+                if (rew64) rew64[a] = r;
             }
             done = steps > c.max_episode_steps;
         }
@@ -510,14 +545,14 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         for (int i = 0; i < 4 && i < N; i++) messages |= (act[i] % 4) << (2 * i);   // MaterialTransport.py:119-120
 #pragma unroll
         for (int a = 0; a < N; a++) {                                       // get_observations (:150-159)
-            float *o = obs + a * D;
-            o[0] = (float)px[a]; o[1] = (float)py[a]; o[2] = (float)load[a];
-            o[3] = (float)zone[0]; o[4] = (float)zone[1];
+            const ObsRow o(obs, obs64, a * D);
+            o.put(0, px[a]); o.put(1, py[a]); o.put(2, (double)load[a]);
+            o.put(3, (double)zone[0]); o.put(4, (double)zone[1]);
 #pragma unroll
-            for (int i = 0; i < 4; i++) o[5 + i] = (float)((messages >> (2 * i)) & 3);
+            for (int i = 0; i < 4; i++) o.put(5 + i, (double)((messages >> (2 * i)) & 3));
             if (c.capability_aware) {
-                o[9] = (float)(a < c.n_fast ? c.small_torque : c.large_torque);
-                o[10] = (float)(a < c.n_fast ? c.fast_step : c.slow_step);
+                o.put(9, (double)(a < c.n_fast ? c.small_torque : c.large_torque));
+                o.put(10, a < c.n_fast ? c.fast_step : c.slow_step);
             }
         }
         double r;
@@ -552,7 +587,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         }
         remaining = zone[0] + zone[1];
 #pragma unroll
-        for (int a = 0; a < N; a++) { rew[a] = (float)r; remaining += load[a]; sci[a * S] = load[a]; }
+        for (int a = 0; a < N; a++) { rew[a] = (float)r; if (rew64) rew64[a] = r; remaining += load[a]; sci[a * S] = load[a]; }
         sci[N * S] = zone[0]; sci[(N + 1) * S] = zone[1]; sci[(N + 2) * S] = messages;
     } else if (SCN == MRB_ARCTIC) {
         uint32_t g[6];
@@ -566,15 +601,15 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             pix[i] = arctic_grid(g, row[i], col[i]);
         }
         const double goalx = goal_col * .25 - 1.5, goaly = (-1 * .25 + .75);  // get_pose_from_cell([1, g])
-        float nb[16];
+        int nb[16];
 #pragma unroll
         for (int i = 0; i < 2; i++) {                                       // agent.py:73-85
             const int left = col[i] > 0 ? col[i] - 1 : col[i], right = col[i] < 11 ? col[i] + 1 : col[i];
             const int up = row[i] > 0 ? row[i] - 1 : row[i], down = row[i] < 7 ? row[i] + 1 : row[i];
-            nb[8 * i + 0] = (float)arctic_grid(g, up, left);   nb[8 * i + 1] = (float)arctic_grid(g, row[i], left);
-            nb[8 * i + 2] = (float)arctic_grid(g, down, left); nb[8 * i + 3] = (float)arctic_grid(g, up, col[i]);
-            nb[8 * i + 4] = (float)arctic_grid(g, down, col[i]); nb[8 * i + 5] = (float)arctic_grid(g, up, right);
-            nb[8 * i + 6] = (float)arctic_grid(g, row[i], right); nb[8 * i + 7] = (float)arctic_grid(g, down, right);
+            nb[8 * i + 0] = arctic_grid(g, up, left);   nb[8 * i + 1] = arctic_grid(g, row[i], left);
+            nb[8 * i + 2] = arctic_grid(g, down, left); nb[8 * i + 3] = arctic_grid(g, up, col[i]);
+            nb[8 * i + 4] = arctic_grid(g, down, col[i]); nb[8 * i + 5] = arctic_grid(g, up, right);
+            nb[8 * i + 6] = arctic_grid(g, row[i], right); nb[8 * i + 7] = arctic_grid(g, down, right);
         }
         at_pix = 0;
 #pragma unroll
@@ -582,16 +617,16 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             at_pix |= pix[a] << (2 * a);
             if (pix[a] == 3) at_reached |= 1 << a;
             constexpr int perm[4][3] = {{1, 2, 3}, {0, 2, 3}, {3, 0, 1}, {2, 0, 1}};   // agent.py:42-69
-            float *o = obs + a * D;
-            o[0] = (float)px[a]; o[1] = (float)py[a]; o[2] = (float)pix[a];
+            const ObsRow o(obs, obs64, a * D);
+            o.put(0, px[a]); o.put(1, py[a]); o.put(2, (double)pix[a]);
 #pragma unroll
             for (int t = 0; t < 3; t++) {
                 const int b = perm[a & 3][t];
-                o[3 + 3 * t] = (float)px[b]; o[4 + 3 * t] = (float)py[b]; o[5 + 3 * t] = (float)pix[b];
+                o.put(3 + 3 * t, px[b]); o.put(4 + 3 * t, py[b]); o.put(5 + 3 * t, (double)pix[b]);
             }
-            o[12] = (float)goalx; o[13] = (float)goaly;
+            o.put(12, goalx); o.put(13, goaly);
 #pragma unroll
-            for (int t = 0; t < 16; t++) o[14 + t] = nb[t];
+            for (int t = 0; t < 16; t++) o.put(14 + t, (double)nb[t]);
         }
         double r;
         if (msg) { r = c.violation_reward; done = true; }
@@ -612,20 +647,22 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             scen_metric = all_reached ? 1 : 0;
         }
 #pragma unroll
-        for (int a = 0; a < N; a++) rew[a] = (float)r;
+        for (int a = 0; a < N; a++) { rew[a] = (float)r; if (rew64) rew64[a] = r; }
         sci[7 * S] = at_pix; sci[8 * S] = at_reached;
     } else {                                                                // Simple (simple.py:155-225)
         const double goalx = scf[0], goaly = scf[S];
 #pragma unroll
         for (int a = 0; a < N; a++) {
-            float *o = obs + a * D;
+            const ObsRow o(obs, obs64, a * D);
             int k = 0;
-            o[k++] = (float)px[a]; o[k++] = (float)py[a];
+            o.put(k++, px[a]); o.put(k++, py[a]);
 #pragma unroll
-            for (int b = 0; b < N; b++) if (b != a) { o[k++] = (float)px[b]; o[k++] = (float)py[b]; }
-            o[k++] = (float)goalx; o[k++] = (float)goaly;
+            for (int b = 0; b < N; b++) if (b != a) { o.put(k++, px[b]); o.put(k++, py[b]); }
+            o.put(k++, goalx); o.put(k++, goaly);
             const double dx = px[a] - goalx, dy = py[a] - goaly;
-            rew[a] = msg ? (float)c.violation_reward : (float)(-(dx * dx + dy * dy) * c.reward_scaler);
+            const double r = msg ? c.violation_reward : -(dx * dx + dy * dy) * c.reward_scaler;
+            rew[a] = (float)r;
+            if (rew64) rew64[a] = r;
         }
         done = msg != 0 || steps > c.max_episode_steps;
     }
@@ -684,10 +721,13 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         const unsigned active = __activemask();
         const int w_it = __reduce_add_sync(active, n_it), w_qp = __reduce_add_sync(active, n_qp);
         const int w_n = __popc(active), w_stall = __reduce_add_sync(active, n_stall);
+        const int w_itw = __reduce_add_sync(active, n_itw), w_sub = __reduce_add_sync(active, n_sub);
         if ((threadIdx.x & 31) == __ffs(active) - 1) {
             atomicAdd(st + MRB_STAT_ENV_STEPS, (double)w_n);
             atomicAdd(st + MRB_STAT_QP_SOLVES, (double)w_qp);
             atomicAdd(st + MRB_STAT_QP_ITERS, (double)w_it);
+            atomicAdd(st + MRB_STAT_QP_ITERS_WARP, (double)w_itw);
+            atomicAdd(st + MRB_STAT_SUBSTEPS, (double)w_sub);
             if (w_stall) atomicAdd(st + MRB_STAT_QP_STALLS, (double)w_stall);
         }
         if (done) {

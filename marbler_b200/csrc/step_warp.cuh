@@ -61,7 +61,7 @@ struct QpWarp {
             const int c = lane + 32 * k;
             pv[k] = c < m;
             int i = 0, rem = pv[k] ? c : 0;
-            while (rem >= N - 1 - i) { rem -= N - 1 - i; i++; }
+            while (i < N - 2 && rem >= N - 1 - i) { rem -= N - 1 - i; i++; }     // i <= N - 2: terminates for every N >= 2
             pi[k] = i; pj[k] = i + 1 + rem;
         }
     }
@@ -452,9 +452,11 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     }
     double v = 0, om = 0, cs = 1, sn = 0, cd = 1, sd = 0, dist = 0;
     if (c.track_dist && prev_valid && me) { const double dx = px - qx, dy = py - qy; dist = sqrt(dx * dx + dy * dy); }
-    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0;
+    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_sub = 0;
     const int UF = c.update_frequency;
+    const double coff = c.collision_offset;
     for (int k = 0; k < UF; k++) {
+        n_sub++;
         if (k > 0) dist += kTimeStep * fabs(v);
         qx = px; qy = py;
         if (k % c.ctrl_period == 0 || c.robotarium) {
@@ -481,10 +483,12 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         bool viol = me && ((px < kArenaXMin) | (px > kArenaXMax) | (py < kArenaYMin) | (py > kArenaYMax));
         const bool viol_b = __any_sync(kFull, viol);
         bool vc = false;
+        // collision points: the centres, or (collision_offset != 0) the points projected along the heading
+        const double cxp = fma(coff, cs, px), cyp = fma(coff, sn, py);
 #pragma unroll
         for (int t = 0; t < PPL; t++) {
-            const double xi_ = __shfl_sync(kFull, px, qp.pi[t]), yi_ = __shfl_sync(kFull, py, qp.pi[t]);
-            const double xj_ = __shfl_sync(kFull, px, qp.pj[t]), yj_ = __shfl_sync(kFull, py, qp.pj[t]);
+            const double xi_ = __shfl_sync(kFull, cxp, qp.pi[t]), yi_ = __shfl_sync(kFull, cyp, qp.pi[t]);
+            const double xj_ = __shfl_sync(kFull, cxp, qp.pj[t]), yj_ = __shfl_sync(kFull, cyp, qp.pj[t]);
             const double dx = xi_ - xj_, dy = yi_ - yj_;
             vc |= qp.pv[t] && (dx * dx + dy * dy) <= p.collision_thr2;
         }
@@ -507,8 +511,10 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
 
     // ---------------------------------------------------------------- scenario tail
     const int D = p.obs_dim;
-    float *obs = p.buf.obs + env * (int64_t)(N * D) + (int64_t)lane * D;
-    float rew = 0.f;
+    const int64_t obs_off = env * (int64_t)(N * D) + (int64_t)lane * D;
+    float *obs = p.buf.obs + obs_off;
+    double *obs64 = p.buf.obs_f64 ? p.buf.obs_f64 + obs_off : nullptr;
+    double rew = 0.0;
     bool done = false;
     int remaining = 0, scen_metric = 0;
 
@@ -552,7 +558,10 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
             const bool capture = __any_sync(kFull, me && act == 4 && d2 <= (pred ? 0.0 : p.capture_thr2));
             if (sense) sensed |= 1u << q;
             if (((sensed >> q) & 1) && capture) { captured |= 1u << q; continue; }
-            if (in_range && (bd < 0.0 || d2 < bd)) { bd = d2; bx = qxp; by = qyp; }
+            if (in_range) {                                 // rounded norms, strict <: agent.py:32-36, misc.py:14-18
+                const double dd = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                if (bd < 0.0 || dd < bd) { bd = dd; bx = qxp; by = qyp; }
+            }
         }
         const int unseen = P - __popc(sensed), left = P - __popc(captured);
         if (lane == 0) { sci[0] = (int32_t)sensed; sci[S] = (int32_t)captured; }
@@ -561,18 +570,18 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         if (me) { sbx[lane] = bx; sby[lane] = by; }
         __syncwarp();
         auto put = [&](int b) {
-            float *o = obs + slot * od;
-            o[0] = (float)spx[b]; o[1] = (float)spy[b]; o[2] = (float)sbx[b]; o[3] = (float)sby[b];
+            const ObsRow o(obs, obs64, slot * od);
+            o.put(0, spx[b]); o.put(1, spy[b]); o.put(2, sbx[b]); o.put(3, sby[b]);
             if (od == 6) {
-                o[4] = (float)(b < c.num_predators ? c.predator_radius : 0.0);
-                o[5] = (float)(b < c.num_predators ? 0.0 : c.capture_radius);
+                o.put(4, b < c.num_predators ? c.predator_radius : 0.0);
+                o.put(5, b < c.num_predators ? 0.0 : c.capture_radius);
             }
             slot++;
         };
         if (me) for_each_block(put);
-        if (msg) { rew = (float)c.violation_reward; done = true; }
+        if (msg) { rew = c.violation_reward; done = true; }
         else {
-            rew = (float)(((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty);
+            rew = ((unseen0 - unseen) * c.sense_reward + (left0 - left) * c.capture_reward) + c.time_penalty;
             done = steps > c.max_episode_steps || left == 0;
         }
         remaining = left; scen_metric = P - left;
@@ -580,20 +589,20 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         uint32_t loaded = (uint32_t)sci[0];
         int slot = 0;
         auto put = [&](int b) {
-            float *o = obs + slot * 3;
-            o[0] = (float)spx[b]; o[1] = (float)spy[b]; o[2] = (float)((loaded >> b) & 1);
+            const ObsRow o(obs, obs64, slot * 3);
+            o.put(0, spx[b]); o.put(1, spy[b]); o.put(2, (double)((loaded >> b) & 1));
             slot++;
         };
         if (me) for_each_block(put);
         bool set_bit = false, clr_bit = false;
-        if (msg) { rew = (float)c.violation_reward; done = true; }
+        if (msg) { rew = c.violation_reward; done = true; }
         else {
             if (me) {
                 const bool green = (lane % 2 == 0), ld = (loaded >> lane) & 1;
                 if (ld) {
-                    if (px < -1.5 + c.goal_width && ((green && py > 0) || (!green && py <= 0))) { rew = (float)c.unload_reward; clr_bit = true; }
+                    if (px < -1.5 + c.goal_width && ((green && py > 0) || (!green && py <= 0))) { rew = c.unload_reward; clr_bit = true; }
                 } else {
-                    if (px > 1.5 - c.goal_width && ((!green && py > 0) || (green && py <= 0))) { rew = (float)c.load_reward; set_bit = true; }
+                    if (px > 1.5 - c.goal_width && ((!green && py > 0) || (green && py <= 0))) { rew = c.load_reward; set_bit = true; }
                 }
             }
             done = steps > c.max_episode_steps;
@@ -608,12 +617,12 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         int messages = 0;
         for (int i = 0; i < 4; i++) messages |= (__shfl_sync(kFull, act, i) % 4) << (2 * i);
         if (me) {
-            float *o = obs;
-            o[0] = (float)px; o[1] = (float)py; o[2] = (float)load; o[3] = (float)zone0; o[4] = (float)zone1;
-            for (int i = 0; i < 4; i++) o[5 + i] = (float)((messages >> (2 * i)) & 3);
+            const ObsRow o(obs, obs64, 0);
+            o.put(0, px); o.put(1, py); o.put(2, (double)load); o.put(3, (double)zone0); o.put(4, (double)zone1);
+            for (int i = 0; i < 4; i++) o.put(5 + i, (double)((messages >> (2 * i)) & 3));
             if (c.capability_aware) {
-                o[9] = (float)(lane < c.n_fast ? c.small_torque : c.large_torque);
-                o[10] = (float)(lane < c.n_fast ? c.fast_step : c.slow_step);
+                o.put(9, (double)(lane < c.n_fast ? c.small_torque : c.large_torque));
+                o.put(10, lane < c.n_fast ? c.fast_step : c.slow_step);
             }
         }
         double r;
@@ -642,7 +651,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
             done = steps > c.max_episode_steps;
             if (!done) done = zone0 == 0 && zone1 == 0 && !__any_sync(kFull, me && load != 0);
         }
-        rew = (float)r;
+        rew = r;
         int tot = load;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
@@ -652,13 +661,14 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     } else {                                            // Simple
         const double goalx = scf[0], goaly = scf[S];
         if (me) {
+            const ObsRow o(obs, obs64, 0);
             int k = 0;
-            obs[k++] = (float)px; obs[k++] = (float)py;
-            for (int b = 0; b < N; b++) if (b != lane) { obs[k++] = (float)spx[b]; obs[k++] = (float)spy[b]; }
-            obs[k] = (float)goalx; obs[k + 1] = (float)goaly;
+            o.put(k++, px); o.put(k++, py);
+            for (int b = 0; b < N; b++) if (b != lane) { o.put(k++, spx[b]); o.put(k++, spy[b]); }
+            o.put(k, goalx); o.put(k + 1, goaly);
         }
         const double dx = px - goalx, dy = py - goaly;
-        rew = msg ? (float)c.violation_reward : (float)(-(dx * dx + dy * dy) * c.reward_scaler);
+        rew = msg ? c.violation_reward : -(dx * dx + dy * dy) * c.reward_scaler;
         done = msg != 0 || steps > c.max_episode_steps;
     }
 
@@ -666,7 +676,8 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     if (me) {
         sf[lane * S] = px; sf[(N + lane) * S] = py; sf[(2 * N + lane) * S] = th;
         sf[(3 * N + lane) * S] = qx; sf[(4 * N + lane) * S] = qy;
-        p.buf.reward[env * N + lane] = rew;
+        p.buf.reward[env * N + lane] = (float)rew;
+        if (p.buf.reward_f64) p.buf.reward_f64[env * N + lane] = rew;
         if (p.buf.dist) p.buf.dist[env * N + lane] = (float)dist;
     }
     if (p.hout.obs) {                       // host mirror of this env's observation block (see step_thread.cuh)
@@ -681,8 +692,8 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
             for (int k = lane; k < words; k += 32) p.hout.obs[base + k] = p.buf.obs[base + k];
         }
     }
-    if (me && p.hout.reward) p.hout.reward[env * N + lane] = rew;
-    float team = me ? rew : 0.f;
+    if (me && p.hout.reward) p.hout.reward[env * N + lane] = (float)rew;
+    float team = me ? (float)rew : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) team += __shfl_xor_sync(kFull, team, o);
     double ep_return = 0.0;
@@ -700,6 +711,8 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
             atomicAdd(st + MRB_STAT_ENV_STEPS, 1.0);
             atomicAdd(st + MRB_STAT_QP_SOLVES, (double)n_qp);
             atomicAdd(st + MRB_STAT_QP_ITERS, (double)n_it);
+            atomicAdd(st + MRB_STAT_QP_ITERS_WARP, (double)n_it);       // one env per warp: nothing to wait for
+            atomicAdd(st + MRB_STAT_SUBSTEPS, (double)n_sub);
             if (n_stall) atomicAdd(st + MRB_STAT_QP_STALLS, (double)n_stall);
             if (done) {
                 atomicAdd(st + MRB_STAT_EPISODES, 1.0);
@@ -733,6 +746,8 @@ inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions,
 template <int SCN>
 inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cudaStream_t s)
 {
+    // ArcticTransport (exactly 4 robots, per-terrain step sizes, grid observations) exists on the thread kernel only
+    if (SCN == MRB_ARCTIC) return cudaErrorNotSupported;
     const int ppl = pairs_per_lane(p.cfg.num_robots);
     if (SCN == MRB_PCP && p.cfg.num_robots == 20 && !std::getenv("MRB_WARP_GENERIC")) return launch_step_warp_ppl<SCN, 6, 20>(p, actions, s);
     if (ppl <= 1) return launch_step_warp_ppl<SCN, 1>(p, actions, s);

@@ -1,0 +1,26 @@
+"""FP64 flop model of the step kernels: useful floating-point operations of a launch from the counters the kernels
+accumulate in the statistics vector (sub-steps executed, controller evaluations = QP solves, interior-point
+iterations, env steps):
+
+    flops = a * substeps + b * qp_solves + c * qp_iterations + d * env_steps
+
+The coefficients are FITTED, per kernel, to instruction counts measured with ncu on the B200
+(smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum, flops = dadd + dmul + 2 dfma) over launches of
+config variants that decorrelate the four counters (update_frequency 15 / 29 / 45, robotarium = True);
+scripts/fp64_flop_model.py collects the data and does the fit, profiles/r02_fp64_flop_model.json holds the raw
+counts, the fit and its residuals.  Thread-level predicated-on counts: lanes idling in a diverged warp do not
+count, so these are the flops the envs needed, not the issue slots the warps spent.
+bench.py multiplies the live counters of the timed region with these coefficients (roofline_fp64.achieved)."""
+
+# (scenario, robots) -> (a, b, c, d)
+COEFFICIENTS = {}
+
+
+def flops(scenario, n_robots, stats):
+    co = COEFFICIENTS.get((scenario, int(n_robots)))
+    if co is None:
+        return None
+    a, b, c, d = co
+    total = a * stats["substeps"] + b * stats["qp_solves"] + c * stats["qp_iterations"] + d * stats["env_steps"]
+    return {"total": total, "model": {"per_substep": a, "per_solve": b, "per_iteration": c, "per_env_step": d,
+                                      "source": "profiles/r02_fp64_flop_model.json (fit to ncu instruction counts)"}}

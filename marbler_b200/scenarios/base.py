@@ -77,7 +77,8 @@ class BatchedScenario(BaseEnv):
         if auto_reset is None:
             auto_reset = self.num_envs > 1
         self.vec = VecEnv(self.scenario, cfg, num_envs=self.num_envs, device=device, seed=seed, env_id0=env_id0,
-                          auto_reset=auto_reset, track_dist=track_dist, collect_stats=collect_stats)
+                          auto_reset=auto_reset, track_dist=track_dist, collect_stats=collect_stats,
+                          f64_outputs=self.num_envs == 1)     # one env: float64 observations / rewards like the reference
         self.num_robots = self.vec.N
         self.num_agent = self.num_robots
         self.visualizer = _NoVisualizer()
@@ -106,6 +107,7 @@ class BatchedScenario(BaseEnv):
             st = sample_reset(self.scenario, self._cfg)
             self.vec.set_state({k: np.asarray(v)[None] for k, v in st.items()})
             self.vec.obs.zero_()
+            self.vec.obs_f64.zero_()
         else:
             self.vec.reset(mask=mask, seed=seed)
         if self.num_envs == 1:                  # e.g. PredatorCapturePrey.py:136: an all-zero observation
@@ -122,8 +124,10 @@ class BatchedScenario(BaseEnv):
             info = self._info_single(code, terminated, int(self.vec.remaining[0].item()))
             if self.vec.dist is not None:
                 info["dist_travelled"] = self.vec.dist[0].cpu().numpy().astype(np.float64)
-            o = obs[0].numpy()
-            return [o[i].copy() for i in range(self.num_robots)], [float(r) for r in rew[0]], \
+            # float64 like the reference (e.g. PredatorCapturePrey.py:176 returns numpy float64 rows and Python floats)
+            o = self.vec.obs_f64[0].cpu().numpy()
+            r = self.vec.reward_f64[0].cpu().numpy()
+            return [o[i].copy() for i in range(self.num_robots)], [float(v) for v in r], \
                 [terminated] * self.num_robots, info
         if isinstance(actions_, torch.Tensor) and actions_.is_cuda:
             obs, rew, done, msg = self.vec.step(actions_)
@@ -142,12 +146,15 @@ class BatchedScenario(BaseEnv):
 
     def get_observations(self, *_):
         """Observations of the most recent step (computed inside the fused step kernel)."""
-        o = self.vec.obs
-        return [o[0, i].cpu().numpy() for i in range(self.num_robots)] if self.num_envs == 1 else o
+        if self.num_envs == 1:
+            o = self.vec.obs_f64[0].cpu().numpy()
+            return [o[i].copy() for i in range(self.num_robots)]
+        return self.vec.obs
 
     def get_rewards(self, *_):
-        r = self.vec.reward
-        return [float(v) for v in r[0].cpu()] if self.num_envs == 1 else r
+        if self.num_envs == 1:
+            return [float(v) for v in self.vec.reward_f64[0].cpu()]
+        return self.vec.reward
 
     get_reward = get_rewards                    # MaterialTransport / ArcticTransport spell it get_reward
 

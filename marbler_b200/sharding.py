@@ -37,6 +37,29 @@ def init_distributed(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank):
+    """Restrict this process to the CPUs NVML reports as local to GPU `local_rank` (its NUMA node).  Call it before
+    anything allocates pinned host memory: pages are placed on the node of the thread that first touches them, and a
+    device->host copy into the far node crosses the inter-socket link (the e2e path of an 8-GPU box is bound by
+    exactly that).  Returns a description for the bench line, or None when NVML / the mask is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": index, "cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception:
+        return None
+
+
 def allreduce_stats(stats):
     """SUM all ranks' statistics vectors (f64 [NUM_STATS]); NCCL over NVLink on GPUs, gloo on CPU."""
     assert stats.numel() == NUM_STATS

@@ -19,7 +19,7 @@ def _ptr(t):
 
 class VecEnv(object):
     def __init__(self, scenario, cfg, num_envs=1, device=None, seed=0, env_id0=0, auto_reset=False,
-                 track_dist=True, collect_stats=True):
+                 track_dist=True, collect_stats=True, f64_outputs=False):
         if not torch.cuda.is_available():
             raise RuntimeError("marbler_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -51,9 +51,12 @@ class VecEnv(object):
         self.remaining = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.dist = torch.zeros((B, N), dtype=torch.float32, device=dev) if track_dist else None
         self.stats = torch.zeros((_lib.NUM_STATS,), dtype=torch.float64, device=dev)
+        # float64 copies of obs / reward (the reference's own precision; used by the single-env drop-in path)
+        self.obs_f64 = torch.zeros((B, N, D), dtype=torch.float64, device=dev) if f64_outputs else None
+        self.reward_f64 = torch.zeros((B, N), dtype=torch.float64, device=dev) if f64_outputs else None
         self._buffers = _lib.Buffers(*[_ptr(t).value for t in (
             self.state_f64, self.state_i32, self.obs, self.reward, self.done, self.message, self.remaining,
-            self.dist, self.stats)])
+            self.dist, self.stats, self.obs_f64, self.reward_f64)])
         _lib.check(self.lib.mrb_bind(self.handle, C.byref(self._buffers)), self.handle)
         self._host = None
 
@@ -129,15 +132,47 @@ class VecEnv(object):
         return self.B * self.N * self.D * 4 + self.B * self.N * 4 + 2 * self.B
 
     # ------------------------------------------------------------------ state (checkpoint / parity injection)
-    def get_state(self):
-        sf = self.state_f64.cpu().numpy()
-        si = self.state_i32.cpu().numpy()
-        return layout.unpack(self.scenario, self.N, self.P, sf, si)
+    def _fields(self, count, names=None, source=None):
+        """numpy arrays + the mrb_state_fields struct pointing at them (arrays from `source` when given)."""
+        wanted = _lib.COMMON_FIELDS + _lib.SCENARIO_FIELDS[self.scenario]
+        arrays, f = {}, _lib.StateFields()
+        f.struct_size = C.sizeof(_lib.StateFields)
+        for name, dt, shape in _lib.STATE_FIELDS:
+            if name not in wanted or (names is not None and name not in names):
+                continue
+            full = (count,) + shape(self.N, self.P)
+            if source is None:
+                a = np.zeros(full, dtype=dt)
+            else:
+                if name not in source:
+                    continue
+                a = np.ascontiguousarray(np.asarray(source[name]).reshape(full), dtype=dt)
+            arrays[name] = a
+            setattr(f, name, a.ctypes.data)
+        return arrays, f
 
-    def set_state(self, st):
-        sf, si = layout.pack(self.scenario, self.N, self.P, st, self.B)
-        self.state_f64.copy_(torch.from_numpy(sf))
-        self.state_i32.copy_(torch.from_numpy(si))
+    def get_state(self, env_lo=0, count=None, names=None):
+        """Per-field state of envs [env_lo, env_lo + count) (mrb_get_state): dict of numpy arrays with a leading
+        env axis, the reference's own state variables (field names and citations: include/marbler_b200.h)."""
+        count = self.B - env_lo if count is None else int(count)
+        arrays, f = self._fields(count, names)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb_get_state(self.handle, int(env_lo), count, C.byref(f), self._stream()), self.handle)
+        return arrays
+
+    def set_state(self, st, env_lo=0, count=None, envs=None):
+        """Overwrite the state of envs [env_lo, env_lo + count) (mrb_set_state) with the fields present in `st`
+        (leading env axis); fields that are absent keep their values.  `envs`: an index array instead of a range -
+        `st` then holds one entry per listed env (each env is written on its own)."""
+        if envs is not None:
+            envs = np.asarray(envs).reshape(-1)
+            for k, e in enumerate(envs):
+                self.set_state({n: np.asarray(v)[k:k + 1] for n, v in st.items()}, env_lo=int(e), count=1)
+            return
+        count = self.B - env_lo if count is None else int(count)
+        arrays, f = self._fields(count, source=st)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb_set_state(self.handle, int(env_lo), count, C.byref(f), self._stream()), self.handle)
 
     def read_stats(self, reset=False):
         v = self.stats.cpu().numpy().copy()
@@ -149,6 +184,14 @@ class VecEnv(object):
     def agent_poses(self):
         """[B, 3, N] view-copy of the unicycle poses (the reference's scenario.agent_poses is (3, N))."""
         return self.state_f64[:3 * self.N].t().reshape(self.B, 3, self.N)
+
+
+def fp64_peak(device=0, milliseconds=200.0):
+    """Measured FP64 rate of independent DFMA chains on `device`, TFLOP/s (mrb_fp64_peak): the roofline the
+    step kernels are compared with."""
+    out = C.c_double()
+    _lib.check(_lib.load().mrb_fp64_peak(int(device), float(milliseconds), C.byref(out)))
+    return out.value
 
 
 def barrier_qp(dxi, xi, barrier_default=False):

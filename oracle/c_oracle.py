@@ -34,7 +34,8 @@ class Config(C.Structure):
             "unload_reward", "goal_width", "zone1_radius", "not_reached_penalty", "dist_multiplier",
             "reward_scaler", "violation_reward")] + \
         [("zone_mu", C.c_double * 2), ("zone_sigma", C.c_double * 2),
-         ("spawn_robots", Spawn), ("spawn_other", Spawn)]
+         ("spawn_robots", Spawn), ("spawn_other", Spawn),
+         ("collision_diameter", C.c_double), ("collision_offset", C.c_double)]
 
 
 def build(force=False):
@@ -97,6 +98,9 @@ def make_config(scenario, cfg):
     c.num_neighbors = g("num_neighbors", 0)
     c.capability_aware = int(bool(g("capability_aware", False)))
     c.LEFT, c.RIGHT, c.UP, c.DOWN = cfg["LEFT"], cfg["RIGHT"], cfg["UP"], cfg["DOWN"]
+    # the rps collision test in force (oracle/shims/rps/robotarium_abc.py; ref_harness applies the same two keys)
+    c.collision_diameter = float(g("rps_collision_diameter", 0.135))
+    c.collision_offset = float(g("rps_collision_offset", 0.0))
     height = cfg["DOWN"] - cfg["UP"]
     if scenario == "PredatorCapturePrey":
         c.N = cfg["predator"] + cfg["capture"]                # PredatorCapturePrey.py:19

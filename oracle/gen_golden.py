@@ -213,9 +213,24 @@ def qp_vectors():
     print("qp_vectors %.1f KB" % (os.path.getsize(path) / 1024.0))
 
 
+PROJECTED = dict(rps_collision_offset=0.025)      # the heading-projected form of rps' collision test
+
+
+def collision_variants():
+    """The same kinds of cases under the other published form of rps' collision test (config keys
+    rps_collision_offset / rps_collision_diameter; oracle/shims/rps/robotarium_abc.py)."""
+    inject("PCP_projected_collision_inject", "PredatorCapturePrey", 192, seed=51, crowd=0.6, **PROJECTED)
+    inject("Warehouse_projected_collision_inject", "Warehouse", 96, seed=52, crowd=0.6, **PROJECTED)
+    rollout("MT_projected_collision_rollout", "MaterialTransport", 60, seed=53, **PROJECTED)
+    inject("PCP20_projected_collision_inject", "PredatorCapturePrey", 24, seed=54, crowd=0.3, **dict(PCP20, **PROJECTED))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["collision_variants"]:         # only the fixtures added in round 2 (the others are unchanged)
+        return collision_variants()
     qp_vectors()
+    collision_variants()
     for i, scn in enumerate(("PredatorCapturePrey", "Warehouse", "MaterialTransport", "ArcticTransport", "Simple")):
         rollout("%s_rollout" % scn, scn, 160, seed=11 + i)
         inject("%s_inject" % scn, scn, 256, seed=21 + i)

@@ -19,7 +19,6 @@
 /* rps RobotariumABC constants (oracle/shims/rps/robotarium_abc.py) */
 static const double TIME_STEP = 0.033;
 static const double MAX_LIN = 0.2;
-static const double COLLISION_DIAMETER = 0.135;
 static const double BX0 = -1.6, BY0 = -1.0, BW = 3.2, BH = 2.0;
 /* controller constants (App. A.6-A.8) */
 static const double PROJ = 0.05, SI_VEL_LIMIT = 0.15, ANG_LIMIT = M_PI, QP_MAG_LIMIT = 0.2;
@@ -436,8 +435,12 @@ void orc_step(const orc_config *c, double *sf, int32_t *si, const int32_t *actio
             if (x < BX0 || x > (BX0 + BW) || y < BY0 || y > (BY0 + BH)) viol_b = 1;
         }
         for (int j = 0; j < N - 1; j++)
-            for (int l = j + 1; l < N; l++)
-                if (norm2(pose[j] - pose[l], pose[N + j] - pose[N + l]) <= COLLISION_DIAMETER) viol_c = 1;
+            for (int l = j + 1; l < N; l++) {
+                double off = c->collision_offset;           /* first_position / second_position of _validate */
+                double x1 = pose[j] + off * cos(pose[2 * N + j]), y1 = pose[N + j] + off * sin(pose[2 * N + j]);
+                double x2 = pose[l] + off * cos(pose[2 * N + l]), y2 = pose[N + l] + off * sin(pose[2 * N + l]);
+                if (norm2(x1 - x2, y1 - y2) <= c->collision_diameter) viol_c = 1;
+            }
         for (int i = 0; i < N; i++) {
             double th = pose[2 * N + i];
             pose[i] = pose[i] + TIME_STEP * cos(th) * vel[i];

@@ -75,6 +75,11 @@ class RefEnv(object):
 
     # ------------------------------------------------------------------ reset / step
     def reset(self):
+        # the rps collision test is not a MARBLER config key (rps hard-codes it); two extra keys select the form the
+        # stand-in applies.  roboEnv builds a new Robotarium at every reset (roboEnv.py:98-112), which reads these.
+        import rps.robotarium_abc as rabc
+        rabc.COLLISION_OFFSET = float(self.cfg.get("rps_collision_offset", 0.0))
+        rabc.COLLISION_DIAMETER = float(self.cfg.get("rps_collision_diameter", 0.135))
         with contextlib.redirect_stdout(self._sink):
             obs = self.wrapper.reset()
         self.scn.env.errors = copy.deepcopy(self.scn.env.robotarium._errors)

@@ -9,6 +9,11 @@ WHEEL_RADIUS = 0.016
 BASE_LENGTH = 0.105
 MAX_LINEAR_VELOCITY = 0.2
 COLLISION_DIAMETER = 0.135
+# Two forms of the collision test exist in published rps revisions and the pinned commit (6bb184e) cannot be read
+# here: centre to centre (offset 0: SURVEY.md App. A.4, what every default fixture uses) and the points projected
+# 0.025 m along each robot's heading.  ref_harness.RefEnv sets the instance attribute from the config keys
+# rps_collision_offset / rps_collision_diameter.
+COLLISION_OFFSET = 0.0
 BOUNDARIES = [-1.6, -1, 3.2, 2]
 
 
@@ -36,6 +41,7 @@ class RobotariumABC(object):
         self.max_wheel_velocity = self.max_linear_velocity / self.wheel_radius
         self.robot_radius = self.robot_diameter / 2
         self.collision_diameter = COLLISION_DIAMETER
+        self.collision_offset = COLLISION_OFFSET
 
         self.velocities = np.zeros((2, number_of_robots))
         self.poses = self.initial_conditions        # NO copy: callers alias the simulator state
@@ -82,7 +88,9 @@ class RobotariumABC(object):
 
         for j in range(N - 1):
             for k in range(j + 1, N):
-                if np.linalg.norm(p[:2, j] - p[:2, k]) <= self.collision_diameter:
+                first_position = p[:2, j] + self.collision_offset * np.array([np.cos(p[2, j]), np.sin(p[2, j])])
+                second_position = p[:2, k] + self.collision_offset * np.array([np.cos(p[2, k]), np.sin(p[2, k])])
+                if np.linalg.norm(first_position - second_position) <= self.collision_diameter:
                     if "collision" in errors:
                         if j in errors["collision"]:
                             errors["collision"][j] += 1

@@ -75,17 +75,27 @@ STALL_ITERS = 25
 
 
 def _resync(env, orc, sf, si, idx):
-    """Copy the oracle's state of envs `idx` into the CUDA env (after an unreproducible solve)."""
-    from marbler_b200 import layout
-    sub = orc.unpack(sf[idx], si[idx])
-    pf, pi = layout.pack(env.scenario, env.N, env.P, sub, len(idx))
-    ti = torch.as_tensor(idx, device=env.device)
-    pf[5 * env.N] = env.state_f64[5 * env.N, ti].cpu().numpy()          # keep the env's own episode return
-    env.state_f64[:, ti] = torch.from_numpy(pf).to(env.device)
-    env.state_i32[:, ti] = torch.from_numpy(pi).to(env.device)
+    """Copy the oracle's state of envs `idx` into the CUDA env (after an unreproducible solve) through
+    mrb_set_state; the env keeps its own episode return (a field the oracle does not carry)."""
+    env.set_state(orc.unpack(sf[idx], si[idx]), envs=idx)
 
 
-def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
+LOCKSTEP_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "lockstep_counts.jsonl")
+
+
+def _log_counts(rec):
+    """Exclusion counts of every lock-step run, one JSON line each (copied to profiles/ from the GPU run)."""
+    import json
+    print("lockstep", json.dumps(rec))
+    try:
+        os.makedirs(os.path.dirname(LOCKSTEP_LOG), exist_ok=True)
+        with open(LOCKSTEP_LOG, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+
+
+def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4, label=None):
     """Same reset (same Philox draws), same random actions, T steps: the CUDA env and the C oracle must
     agree at every step (discrete bit-exact, poses 1e-5), including across auto-resets.
 
@@ -100,7 +110,8 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
     env = _vec(scenario, cfg, B, seed=5, auto_reset=True)
     orc = oracle_lib.COracle(scenario, cfg)
     env.reset()
-    sf, si = orc.reset_flat(B, seed=5, threads=8)
+    threads = os.cpu_count() or 8
+    sf, si = orc.reset_flat(B, seed=5, threads=threads)
     rng = np.random.RandomState(0)
     st = env.get_state()
     ost = orc.unpack(sf, si)
@@ -110,7 +121,7 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
     for t in range(T):
         a = rng.randint(0, orc.n_actions, size=(B, orc.N)).astype(np.int32)
         env.step(torch.as_tensor(a, device=env.device))
-        obs, rew, dist, out_i = orc.step_flat(sf, si, a, auto_reset=True, seed=5, threads=8)
+        obs, rew, dist, out_i = orc.step_flat(sf, si, a, auto_reset=True, seed=5, threads=threads)
         ok = out_i[:, 5] < STALL_ITERS
         n_stalled += int((~ok).sum())
         assert np.array_equal(env.message.cpu().numpy()[ok], out_i[ok, 0]), t
@@ -150,6 +161,11 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4):
         n_done += int(out_i[ok, 1].sum())
         n_msg += int((out_i[ok, 0] != 0).sum())
     stats = env.read_stats()
+    _log_counts({"case": label or scenario, "scenario": scenario, "overrides": overrides or {}, "envs": B, "steps": T,
+                 "env_steps": B * T, "excluded_stalled_solves": n_stalled, "loose_pose_env_steps": n_loose,
+                 "knn_tie_env_steps": n_tie, "episodes_finished": n_done, "violations": n_msg,
+                 "qp_iterations": stats["qp_iterations"], "qp_iterations_warp": stats["qp_iterations_warp"]})
+    assert stats["substeps"] <= B * T * cfg["update_frequency"] and stats["qp_iterations_warp"] >= stats["qp_iterations"]
     assert n_stalled <= max(2, int(stall_frac * B * T)), n_stalled
     assert n_loose <= max(2, int(1e-4 * B * T)), n_loose
     assert n_tie <= max(4, int(5e-2 * B * T)), n_tie
@@ -187,6 +203,116 @@ def test_other_team_sizes_and_options_lockstep(oracle_lib, scenario, overrides):
     """Team sizes / options the reference fixtures do not cover, against the C oracle (which is pinned to the
     reference for N = 4, 6, 20): every kernel dispatch path (thread N = 2..6, warp N = 7..32)."""
     _lockstep(oracle_lib, scenario, 1024, 25, overrides=overrides, stall_frac=2e-2)
+
+
+PCP20 = dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)
+
+
+def test_lockstep_baseline_config2_full_size(oracle_lib):
+    """BASELINE.json configs[1] literally: PredatorCapturePrey, 65,536 envs, barrier certificates on, random actions,
+    20 steps against the oracle with the bit-exact event / done / message / flag / counter check at every step."""
+    _lockstep(oracle_lib, "PredatorCapturePrey", 65536, 20, label="config2 PCP 65536")
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["specialised", "generic"])
+def test_lockstep_20_robots(oracle_lib, generic, monkeypatch):
+    """BASELINE.json configs[4]'s team (10 predators + 10 capture agents, K = 3 nearest neighbours): 4,096 envs x 25
+    steps on the compile-time-specialised warp kernel and on the generic one (MRB_WARP_GENERIC is read per launch)."""
+    if generic:
+        monkeypatch.setenv("MRB_WARP_GENERIC", "1")
+    else:
+        monkeypatch.delenv("MRB_WARP_GENERIC", raising=False)
+    _lockstep(oracle_lib, "PredatorCapturePrey", 4096, 25, overrides=PCP20, stall_frac=2e-3,
+              label="config5 PCP20 " + ("generic" if generic else "specialised"))
+
+
+@pytest.mark.parametrize("scenario", ["Warehouse", "MaterialTransport", "ArcticTransport"])
+def test_lockstep_full_size_other_configs(oracle_lib, scenario):
+    """BASELINE.json configs[2], [3] at 65,536 envs, a few steps (the CPU oracle needs ~0.3 s per step here)."""
+    _lockstep(oracle_lib, scenario, 65536, 6, stall_frac=5e-3 if scenario == "MaterialTransport" else 1e-4,
+              label="full size " + scenario)
+
+
+def test_projected_collision_form_lockstep(oracle_lib):
+    """The other published form of rps' collision test (heading-projected points, offset 0.025) in closed loop."""
+    _lockstep(oracle_lib, "PredatorCapturePrey", 4096, 40, overrides=dict(rps_collision_offset=0.025), label="PCP projected collision")
+    _lockstep(oracle_lib, "Warehouse", 2048, 40, overrides=dict(rps_collision_offset=0.025), label="Warehouse projected collision")
+
+
+def test_state_access_through_the_c_abi():
+    """mrb_get_state / mrb_set_state against the raw SoA rows (marbler_b200/layout.py is the independent description
+    of the row layout): every field of every scenario, env ranges, and fields left NULL keep their values."""
+    from marbler_b200 import layout
+    for scenario, B in SCN_B:
+        g = gu.Golden(scenario + "_rollout")
+        env = _vec(scenario, g.cfg, 300, seed=3, auto_reset=True)
+        env.reset()
+        gen = torch.Generator(device="cuda:0").manual_seed(1)
+        for _ in range(5):
+            env.step(torch.randint(0, env.n_actions, (300, env.N), generator=gen, device="cuda:0", dtype=torch.int32))
+        torch.cuda.synchronize()
+        raw = layout.unpack(scenario, env.N, env.P, env.state_f64.cpu().numpy(), env.state_i32.cpu().numpy())
+        st = env.get_state()
+        assert set(st) == set(raw), (set(st) ^ set(raw))
+        for k in raw:
+            assert np.array_equal(np.asarray(st[k]).astype(np.float64), np.asarray(raw[k]).astype(np.float64)), (scenario, k)
+        part = env.get_state(env_lo=37, count=100)
+        for k in raw:
+            assert np.array_equal(part[k], st[k][37:137]), (scenario, k)
+        # write a permuted copy back through the C ABI, compare the raw rows with the independent packer
+        perm = np.random.RandomState(0).permutation(300)
+        env.set_state({k: v[perm] for k, v in st.items()})
+        pf, pi = layout.pack(scenario, env.N, env.P, {k: v[perm] for k, v in st.items()}, 300)
+        assert np.array_equal(env.state_f64.cpu().numpy(), pf) and np.array_equal(env.state_i32.cpu().numpy(), pi)
+        # partial update: only poses of envs [10, 20); everything else untouched
+        before = env.get_state()
+        new = before["poses"][10:20] + 0.25
+        env.set_state({"poses": new}, env_lo=10, count=10)
+        after = env.get_state()
+        assert np.array_equal(after["poses"][10:20], new)
+        after["poses"][10:20] = before["poses"][10:20]
+        for k in before:
+            assert np.array_equal(after[k], before[k]), (scenario, k)
+        env.set_state({k: v[[5, 200]] for k, v in st.items()}, envs=[7, 250])
+        again = env.get_state()
+        for k in st:
+            assert np.array_equal(again[k][7], st[k][5]) and np.array_equal(again[k][250], st[k][200]), (scenario, k)
+
+
+def test_single_env_returns_float64_like_the_reference(oracle_lib):
+    """num_envs == 1: observations are float64 rows and rewards Python floats at full precision (the reference:
+    PredatorCapturePrey.py:176), not values rounded through the float32 buffers of the batched path."""
+    import marbler_b200
+    for scenario in ("PredatorCapturePrey", "Warehouse", "MaterialTransport", "ArcticTransport", "Simple"):
+        env = marbler_b200.make("robotarium_gym:%s-v0" % scenario, seed=5)
+        env.reset()
+        scn = env.env
+        orc = oracle_lib.COracle(scenario, scn._cfg)
+        st = {k: v[0] for k, v in scn.get_state().items()}
+        a = [1, 3, 0, 2, 4, 1][:scn.num_robots]
+        obs, rew, done, info = env.step(a)
+        out, _ = orc.step({k: v for k, v in st.items() if k not in ("episode_return",)}, a)
+        assert all(o.dtype == np.float64 for o in obs) and all(isinstance(r, float) for r in rew)
+        assert np.abs(np.asarray(obs) - out["obs"]).max() < 1e-9, scenario
+        assert np.abs(np.asarray(rew) - out["reward"]).max() < 1e-9, scenario
+        assert np.abs(np.asarray(scn.get_observations()) - out["obs"]).max() < 1e-9
+        if scenario == "PredatorCapturePrey":
+            assert rew[0] == out["reward"][0] == -0.05          # not float32(-0.05) = -0.0500000007
+
+
+def test_fp64_peak_and_solver_statistics():
+    from marbler_b200.vec_env import fp64_peak
+    tf = fp64_peak(0, 100.0)
+    assert 15.0 < tf < 60.0, tf                                  # B200: ~37-40 TFLOP/s nominal
+    g = gu.Golden("PredatorCapturePrey_rollout")
+    env = _vec("PredatorCapturePrey", g.cfg, 8192, seed=1, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device="cuda:0").manual_seed(1)
+    for _ in range(10):
+        env.step(torch.randint(0, 5, (8192, 4), generator=gen, device="cuda:0", dtype=torch.int32))
+    s = env.read_stats()
+    assert s["env_steps"] == 81920 and 0 < s["substeps"] <= 81920 * g.cfg["update_frequency"]
+    assert 1.0 <= s["qp_iterations_warp"] / s["qp_iterations"] < 2.0     # divergence overhead of the solver loop
 
 
 @pytest.mark.parametrize("scenario", [s for s, _ in SCN_B])

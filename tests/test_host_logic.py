@@ -23,7 +23,7 @@ def lib():
 def test_library_exports_every_declared_symbol(lib):
     from marbler_b200 import _lib
     header = open(os.path.join(ROOT, "include", "marbler_b200.h")).read()
-    declared = set(re.findall(r"\b(mrb_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mrb_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS)
     raw = C.CDLL(_lib.LIB_PATH)
     for s in declared:
@@ -52,6 +52,11 @@ def test_create_rejects_bad_configs(lib):
     h = C.c_void_p()
     assert lib.mrb_create(C.byref(c), 0, 16, 0, C.byref(h)) == -1
     assert b"ABI" in lib.mrb_last_error(None)
+    # a single robot has no pair constraint (and the warp kernel's pair decode assumes N >= 2)
+    one = config.make_config("Simple", dict(config.load_yaml(config.default_config_path("Simple")), n_agents=1))
+    assert lib.mrb_create(C.byref(one), 0, 16, 0, C.byref(h)) == -1 and b"[2, 32]" in lib.mrb_last_error(None)
+    bad = config.make_config("PredatorCapturePrey", dict(cfg, rps_collision_diameter=0.0))
+    assert lib.mrb_create(C.byref(bad), 0, 16, 0, C.byref(h)) == -1 and b"collision_diameter" in lib.mrb_last_error(None)
     with pytest.raises(ValueError):                     # rps asserts the spawn grid has room
         config.make_config("PredatorCapturePrey", dict(cfg, predator=10, capture=10))
     with pytest.raises(ValueError):
@@ -72,7 +77,8 @@ def test_config_matches_oracle_config(oracle_lib, name):
             "max_episode_steps", "num_neighbors", "capability_aware", "num_prey", "num_predators", "n_fast",
             "small_torque", "large_torque", "step_dist", "fast_step", "slow_step", "predator_radius",
             "capture_radius", "time_penalty", "sense_reward", "capture_reward", "load_reward", "unload_reward",
-            "goal_width", "zone1_radius", "not_reached_penalty", "dist_multiplier", "reward_scaler", "violation_reward"]
+            "goal_width", "zone1_radius", "not_reached_penalty", "dist_multiplier", "reward_scaler", "violation_reward",
+            "collision_diameter", "collision_offset"]
     for k in same:
         assert getattr(mine, k) == getattr(ref, k), k
     for sp in ("spawn_robots", "spawn_other"):
