@@ -12,8 +12,17 @@ counts, the fit and its residuals.  Thread-level predicated-on counts: lanes idl
 count, so these are the flops the envs needed, not the issue slots the warps spent.
 bench.py multiplies the live counters of the timed region with these coefficients (roofline_fp64.achieved)."""
 
-# (scenario, robots) -> (a, b, c, d)
-COEFFICIENTS = {}
+# (scenario, robots) -> (a, b, c, d); fit residuals <= 0.6 % over 24 launches per kernel (profiles/r02_fp64_flop_model.json)
+COEFFICIENTS = {
+    ("PredatorCapturePrey", 4): (118.3, 1923.1, 879.0, 187.9),
+    ("Simple", 4): (118.2, 1923.5, 878.9, 88.0),
+    ("MaterialTransport", 4): (117.7, 1477.6, 937.3, 80.4),
+    ("ArcticTransport", 4): (116.0, 1230.8, 967.4, 124.8),
+    ("Warehouse", 6): (202.0, 2435.3, 3304.0, 198.0),
+    # one env per warp: the counts include the arithmetic every lane repeats (e.g. the diagonal-block factorisation is
+    # run by all 32 lanes and one result is kept), i.e. executed rather than minimal flops
+    ("PredatorCapturePrey", 20): (1462.0, 67507.3, 84959.0, 22960.2),
+}
 
 
 def flops(scenario, n_robots, stats):

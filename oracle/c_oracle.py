@@ -266,6 +266,13 @@ class COracle(object):
         _threaded(run, B, threads)
         return sf, si
 
+    def reset_envs(self, sf, si, envs, seed=0, env_id0=0):
+        """Re-sample the listed envs in place (what auto_reset does inside step_flat, as a separate call)."""
+        L = lib()
+        for b in envs:
+            b = int(b)
+            L.orc_reset_batch(self.c, 1, int(seed), int(env_id0 + b), _ptr(sf[b:], C.c_double), _ptr(si[b:], C.c_int32))
+
     # ---------------------------------------------------------------- dict drivers (tests)
     def step(self, st, actions):
         """Same contract as RefEnv.step_from: (outputs, post-state), single env or batched."""

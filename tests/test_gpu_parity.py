@@ -121,7 +121,9 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4, label
     for t in range(T):
         a = rng.randint(0, orc.n_actions, size=(B, orc.N)).astype(np.int32)
         env.step(torch.as_tensor(a, device=env.device))
-        obs, rew, dist, out_i = orc.step_flat(sf, si, a, auto_reset=True, seed=5, threads=threads)
+        obs, rew, dist, out_i = orc.step_flat(sf, si, a, auto_reset=False, seed=5, threads=threads)
+        final_poses = orc.unpack(sf, si)["poses"] if knn else None       # the poses the observations were built from
+        orc.reset_envs(sf, si, np.where(out_i[:, 1] != 0)[0], seed=5)    # auto-reset, as the step kernel does
         ok = out_i[:, 5] < STALL_ITERS
         n_stalled += int((~ok).sum())
         assert np.array_equal(env.message.cpu().numpy()[ok], out_i[ok, 0]), t
@@ -143,7 +145,7 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4, label
             # spawn grid) two neighbours are EXACTLY equidistant and the order is decided by the last bit of
             # the integrated poses (the reference's own argpartition order is unspecified there): skip the obs
             # check for envs with such a tie, count them
-            P = ost["poses"]
+            P = final_poses
             d = np.hypot(P[:, 0, :, None] - P[:, 0, None, :], P[:, 1, :, None] - P[:, 1, None, :])
             ds = np.sort(d, axis=2)
             tie = (np.diff(ds[:, :, 1:], axis=2) < 1e-9).any(axis=(1, 2))
