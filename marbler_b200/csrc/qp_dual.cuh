@@ -171,7 +171,7 @@ struct QpDual {
 #pragma unroll
         for (int a = 0; a < n; a++) { const double qa = q.get(a); qq = fma(qa, qa, qq); }
         // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2
-        const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
+        const double feas_x2 = 1e-4 * dmax(qq, 1.0), feas_z2 = 1e-4 * dmax(hh, 1.0);
 
         // ---- default starting point [P G'; G -I][x; z] = [-q; h]:  (1/2 GG' + I) z = -h - 1/2 G q,  x = -1/2 (q + G'z)
         factor([](int) { return 1.0; });
@@ -191,10 +191,10 @@ struct QpDual {
             const double zc = g - h.get(c);
             z.set(c, zc);
             ss = fma(zc, zc, ss);
-            ts = fmax(ts, zc);
-            tz = fmax(tz, -zc);
+            ts = dmax(zc, ts);
+            tz = dmax(-zc, tz);
         });
-        const double nrm = fmax(sqrt(ss), 1.0);
+        const double nrm = dmax(sqrt(ss), 1.0);
         const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;
 #pragma unroll
@@ -259,11 +259,11 @@ struct QpDual {
                 const double dsc = -sc - dd.get(c) * dz[c];
                 const double p = dsc * dz[c];
                 dsdz += p;
-                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dz[c] * inv_z(c)));
+                tmax = dmax(dmax(-dsc * inv_s(c), -dz[c] * inv_z(c)), tmax);
                 pp.set(c, p);                                  // keep only the Mehrotra correction term
             }
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);          // t == 0 ? 1 : min(1, 1/t)
-            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
+            const double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
             // corrector (rc = -s.z - ds_aff.dz_aff + sigma mu)
 #pragma unroll
@@ -277,7 +277,7 @@ struct QpDual {
 #pragma unroll
             for (int c = 0; c < m; c++) {
                 const double dsc = corr.get(c) - s.get(c) - dd.get(c) * dz[c];
-                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dz[c] * inv_z(c)));
+                tmax = dmax(dmax(-dsc * inv_s(c), -dz[c] * inv_z(c)), tmax);
             }
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);          // t == 0 ? 1 : min(1, 0.99/t)
             // dx = -1/2 (rx + G'dz)

@@ -259,7 +259,7 @@ struct QpThread {
 #pragma unroll
             for (int a = 0; a < n; a++) qq += q[a] * q[a];
         }
-        const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
+        const double feas_x2 = 1e-4 * dmax(qq, 1.0), feas_z2 = 1e-4 * dmax(hh, 1.0);
 
         // ---- default starting point: (2I + G'G) x = -q + G'h ; z = Gx - h ; s = -z ; shift
         factor([](int) { return 1.0; });
@@ -272,10 +272,10 @@ struct QpThread {
             const double zc = gx - h.get(c);
             z.set(c, zc);
             ss += zc * zc;
-            ts = fmax(ts, zc);                // max(-s) = max(z)
-            tz = fmax(tz, -zc);
+            ts = dmax(zc, ts);                // max(-s) = max(z)
+            tz = dmax(-zc, tz);
         });
-        const double nrm = fmax(sqrt(ss), 1.0);
+        const double nrm = dmax(sqrt(ss), 1.0);
         const double s_shift = ts >= -1e-8 * nrm ? 1.0 + ts : 0.0, z_shift = tz >= -1e-8 * nrm ? 1.0 + tz : 0.0;
         const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;
@@ -344,10 +344,10 @@ struct QpThread {
                 const double pr = dsc * dzc;                 // Mehrotra correction term
                 t2.set(c, pr);
                 dsdz += pr;
-                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dzc * inv_z(c)));
+                tmax = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tmax);
             });
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);
-            double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
+            double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
 #pragma unroll
             for (int c = 0; c < m; c++) t2.set(c, (sigmamu - t2.get(c)) * inv_s(c));         // (rc + s.z)/s
@@ -360,7 +360,7 @@ struct QpThread {
                 const double dsc = -rz.get(c) - gd;
                 const double dzc = fma(-w.get(c), dsc, t2.get(c) - z.get(c));                 // (rc - z.ds)/s
                 if (!MRB_QP_RECOMPUTE) { ds.set(c, dsc); dz.set(c, dzc); }
-                tmax = fmax(tmax, fmax(-dsc * inv_s(c), -dzc * inv_z(c)));
+                tmax = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tmax);
             });
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);
             gap = 0.0;

@@ -299,9 +299,10 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         generate_goal(c, agent_step_size<SCN, N>(c, i, at_pix), a, px[i], py[i], gx[i], gy[i]);
     }
 
-    double v[N], om[N], cs[N], sn[N], cd[N], sd[N], dist[N];
+    // dtv = dt v, dtw = dt omega: the velocities in force, pre-multiplied by the time step
+    double dtv[N], dtw[N], cs[N], sn[N], cd[N], sd[N], dist[N];
 #pragma unroll
-    for (int i = 0; i < N; i++) { v[i] = 0.0; om[i] = 0.0; cs[i] = 1.0; sn[i] = 0.0; cd[i] = 1.0; sd[i] = 0.0; dist[i] = 0.0; }
+    for (int i = 0; i < N; i++) dist[i] = 0.0;
     if (c.track_dist && prev_valid) {             // roboEnv.py:55-56 at sub-step 0
 #pragma unroll
         for (int i = 0; i < N; i++) {
@@ -309,19 +310,15 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             dist[i] = sqrt(dx * dx + dy * dy);
         }
     }
-    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_itw = 0, n_sub = 0;
+    int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_itw = 0;
     const int UF = c.update_frequency;
     const double coff = c.collision_offset;
-    for (int k = 0; k < UF; k++) {                // roboEnv.py:52
-        n_sub++;
-        // :55-56 for k >= 1: |pose_k - pose_{k-1}| = dt |v_{k-1}| (c^2 + s^2 = 1)
-        if (k > 0) {
-#pragma unroll
-            for (int i = 0; i < N; i++) dist[i] += kTimeStep * fabs(v[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < N; i++) { qx[i] = px[i]; qy[i] = py[i]; }      // :59
-        if (k % c.ctrl_period == 0 || c.robotarium) {                       // :63-65
+    auto wrap = [](double t) { return t > kPi ? t - kTwoPi : (t < -kPi ? t + kTwoPi : t); };
+    // roboEnv.py:52-96 as two nested loops: a controller evaluation (k % 15 == 0, or every sub-step on the Robotarium,
+    // :63-65), then the sub-steps that run with its velocities.  The inner loop is validation + Euler update only.
+    int k = 0;
+    while (k < UF) {
+        {
             double xix[N], xiy[N], ux[N], uy[N];
 #pragma unroll
             for (int i = 0; i < N; i++) {
@@ -346,51 +343,77 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             }
 #pragma unroll
             for (int i = 0; i < N; i++) {                                   // si_to_uni_dyn (A.7) + saturation (A.2)
-                double vv = cs[i] * ux[i] + sn[i] * uy[i];
+                const double vv = cs[i] * ux[i] + sn[i] * uy[i];
                 double ww = (1.0 / kProjectionDistance) * (-sn[i] * ux[i] + cs[i] * uy[i]);
                 ww = clampd(ww, -kAngularLimit, kAngularLimit);
-                v[i] = clampd(vv, -kMaxLinearVelocity, kMaxLinearVelocity);
-                om[i] = clampd(ww, -kMaxAngularVelocity, kMaxAngularVelocity);
-                sincos(kTimeStep * om[i], &sd[i], &cd[i]);
+                dtv[i] = kTimeStep * clampd(vv, -kMaxLinearVelocity, kMaxLinearVelocity);
+                dtw[i] = kTimeStep * clampd(ww, -kMaxAngularVelocity, kMaxAngularVelocity);
+                small_sincos(dtw[i], sd[i], cd[i]);
             }
         }
-        // Robotarium.step (A.3): _validate (A.4) on the entering pose, then Euler update in place
-        bool viol_b = false, viol_c = false;
+        const int left = UF - k;
+        const int run = c.robotarium ? 1 : (c.ctrl_period < left ? c.ctrl_period : left);
+        int since = 0;                             // updates made with these velocities
+        for (int j = 0; j < run; j++) {
+            // Robotarium.step (A.3): _validate (A.4) on the entering pose, then Euler update in place
+            bool viol_b = false;
 #pragma unroll
-        for (int i = 0; i < N; i++)
-            viol_b |= (px[i] < kArenaXMin) | (px[i] > kArenaXMax) | (py[i] < kArenaYMin) | (py[i] > kArenaYMax);
-        {
+            for (int i = 0; i < N; i++)
+                viol_b |= (px[i] < kArenaXMin) | (px[i] > kArenaXMax) | (py[i] < kArenaYMin) | (py[i] > kArenaYMax);
             // collision points: the centres, or (collision_offset != 0) the points projected along the heading;
-            // (cs, sn) is the heading of the entering pose here (fresh at k = 0, advanced with the pose since)
+            // (cs, sn) is the heading of the entering pose (fresh at the evaluation, advanced with the pose since).
+            // A pair collides when thr2 - |d|^2 >= 0, i.e. when the sign bit of that difference is clear: the bits
+            // are AND-ed in the integer pipe (one FP64 compare per pair costs more, and the compiler would turn an
+            // OR of compares into a chain of NaN-aware fmin)
             double cxp[N], cyp[N];
 #pragma unroll
             for (int i = 0; i < N; i++) { cxp[i] = fma(coff, cs[i], px[i]); cyp[i] = fma(coff, sn[i], py[i]); }
+            int clear = -1;
 #pragma unroll
             for (int i = 0; i < N - 1; i++)
 #pragma unroll
-                for (int j = i + 1; j < N; j++) {
-                    const double dx = cxp[i] - cxp[j], dy = cyp[i] - cyp[j];
-                    viol_c |= (dx * dx + dy * dy) <= p.collision_thr2;
+                for (int jj = i + 1; jj < N; jj++) {
+                    const double dx = cxp[i] - cxp[jj], dy = cyp[i] - cyp[jj];
+                    clear &= __double2hiint(fma(-dy, dy, fma(-dx, dx, p.collision_thr2)));
                 }
+            const bool viol_c = clear >= 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                px[i] = fma(dtv[i], cs[i], px[i]);
+                py[i] = fma(dtv[i], sn[i], py[i]);
+                th[i] += dtw[i];
+                const double c2 = cs[i] * cd[i] - sn[i] * sd[i];           // heading advanced by dt*omega
+                sn[i] = sn[i] * cd[i] + cs[i] * sd[i];
+                cs[i] = c2;
+            }
+            since++;
+            if (c.penalize_violations && (viol_c || viol_b)) {              // roboEnv.py:82-94
+                msg = (viol_c ? 1 : 0) + (viol_b ? 2 : 0);
+                break;
+            }
         }
+        k += since;
+        // roboEnv.py:55-56 adds |pose_k - pose_{k-1}| = dt |v_{k-1}| (c^2 + s^2 = 1) at every sub-step k >= 1, i.e. one
+        // sub-step late: the last update of a step that ran to the end is counted by the NEXT step (through the
+        // stored previous pose); after a violation roboEnv.py:93 adds it right away
+        const double cnt = (double)((msg || k < UF) ? since : since - 1);
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            px[i] = px[i] + kTimeStep * cs[i] * v[i];
-            py[i] = py[i] + kTimeStep * sn[i] * v[i];
-            double t = th[i] + kTimeStep * om[i];
-            // atan2(sin t, cos t) for |t| < pi + 0.12: wrap into (-pi, pi]
-            t = t > kPi ? t - kTwoPi : (t < -kPi ? t + kTwoPi : t);
-            th[i] = t;
-            const double c2 = cs[i] * cd[i] - sn[i] * sd[i];               // heading advanced by dt*omega
-            sn[i] = sn[i] * cd[i] + cs[i] * sd[i];
-            cs[i] = c2;
+            dist[i] = fma(cnt, fabs(dtv[i]), dist[i]);
+            // the reference wraps the heading with atan2(sin, cos) after every sub-step; |dt omega| <= 0.12, so the sum
+            // of up to ctrl_period increments is brought back into (-pi, pi] by one conditional +-2 pi
+            th[i] = wrap(th[i]);
         }
-        if (c.penalize_violations && (viol_c || viol_b)) {                  // roboEnv.py:82-94
-            msg = (viol_c ? 1 : 0) + (viol_b ? 2 : 0);
+        if (msg) break;
+    }
+    const int n_sub = k;
+    // roboEnv.py:59 previous_pose = the pose entering the last sub-step that ran: the final pose stepped back by that
+    // update (heading rotated back by dt*omega); agrees with a stored copy to an ulp and costs no registers in the loop
 #pragma unroll
-            for (int i = 0; i < N; i++) dist[i] += kTimeStep * fabs(v[i]);
-            break;
-        }
+    for (int i = 0; i < N; i++) {
+        const double cp = cs[i] * cd[i] + sn[i] * sd[i], sp = sn[i] * cd[i] - cs[i] * sd[i];
+        qx[i] = fma(-dtv[i], cp, px[i]);
+        qy[i] = fma(-dtv[i], sp, py[i]);
     }
 
     // ---------------------------------------------------------------- scenario tail (order matters)

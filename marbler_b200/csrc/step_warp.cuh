@@ -28,7 +28,7 @@ __device__ __forceinline__ double warp_sum(double v)
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = dmax(__shfl_xor_sync(kFull, v, o), v);
     return v;
 }
 __device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }   // a < b
@@ -260,7 +260,7 @@ struct QpWarp {
         const double qq = warp_sum(lane < N ? 4.0 * (ux * ux + uy * uy) : 0.0);
         hh = warp_sum(hh);
         // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2: cvxopt's residual tests without sqrt / division
-        const double feas_x2 = 1e-4 * fmax(1.0, qq), feas_z2 = 1e-4 * fmax(1.0, hh);
+        const double feas_x2 = 1e-4 * dmax(qq, 1.0), feas_z2 = 1e-4 * dmax(hh, 1.0);
 
         // ---- default starting point
         factor();
@@ -277,11 +277,11 @@ struct QpWarp {
                 z[k] -= h[k];
                 s[k] = -z[k];
                 ss = fma(z[k], z[k], ss);
-                ts = fmax(ts, z[k]);
-                tz = fmax(tz, -z[k]);
+                ts = dmax(z[k], ts);
+                tz = dmax(-z[k], tz);
             } else { s[k] = 1.0; z[k] = 1.0; }
         ss = warp_sum(ss); ts = warp_max(ts); tz = warp_max(tz);
-        const double nrm = fmax(sqrt(ss), 1.0);
+        const double nrm = dmax(sqrt(ss), 1.0);
         double gap = 0.0;
 #pragma unroll
         for (int k = 0; k < PPL; k++)
@@ -355,11 +355,11 @@ struct QpWarp {
                     const double dz = -z[k] - pw[lane + 32 * k] * ds;
                     t2[k] = ds * dz;
                     dsdz += t2[k];
-                    tmax = fmax(tmax, fmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])));
+                    tmax = dmax(dmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])), tmax);
                 } else t2[k] = 0.0;
             dsdz = warp_sum(dsdz); tmax = warp_max(tmax);
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);            // t == 0 ? 1 : min(1, 1/t)
-            const double sg = fmin(1.0, fmax(0.0, 1.0 - step + dsdz * fast_rcp(gap) * (step * step)));
+            const double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
             // corrector
             __syncwarp();
@@ -380,7 +380,7 @@ struct QpWarp {
                 if (pv[k]) {
                     const double ds = -rz[k] - gv[k];
                     const double dz = fma(-pw[lane + 32 * k], ds, t2[k] - z[k]);
-                    tmax = fmax(tmax, fmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])));
+                    tmax = dmax(dmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])), tmax);
                 }
             tmax = warp_max(tmax);
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);           // t == 0 ? 1 : min(1, 0.99/t)
