@@ -82,28 +82,28 @@ struct QpDual {
     __device__ static constexpr int pair_i(int c) { int i = 0; while (c >= N - 1 - i) { c -= N - 1 - i; i++; } return i; }
     __device__ static constexpr int pair_j(int c) { int i = 0; while (c >= N - 1 - i) { c -= N - 1 - i; i++; } return i + 1 + c; }
 
-    // L := chol(1/2 G G' + diag(d)), row by row: row i is built in registers from the rows above it (each earlier
-    // entry is read once per later row), then stored
+    // L := chol(1/2 G G' + diag(d)), column by column (left-looking): pivot k from its own row, then the entries below
+    // it, which are independent of each other.  The Gram entries are formed where they are consumed (never stored).
+    // Per column the dependent chain is (last product of the sums) -> rsqrt -> scale, 72 cycles, against a chain that
+    // grows with the row index in a row-by-row order (measured latencies: profiles/r02_fp64_latency_microbench.txt).
     template <typename D>
     __device__ __forceinline__ void factor(D &&d)
     {
-        static_for<0, m>([&](auto I_) {
-            constexpr int i = decltype(I_)::value;
-            double row[i > 0 ? i : 1] = {};
-            static_for<0, i>([&](auto J_) {
-                constexpr int j = decltype(J_)::value;
-                double v = gram<i, j>();
+        static_for<0, m>([&](auto K_) {
+            constexpr int k = decltype(K_)::value;
+            const double a = ax.get(k), b = ay.get(k);
+            double dk = fma(a, a, b * b) + d(k);                                    // 1/2 |g_k|^2 = |a_k|^2
 #pragma unroll
-                for (int k = 0; k < j; k++) v = fma(-row[k], L.get(low(j, k)), v);
-                row[j] = v * invd[j];
+            for (int j = 0; j < k; j++) { const double l = L.get(low(k, j)); dk = fma(-l, l, dk); }
+            const double r = fast_rsqrt(dk);
+            invd[k] = r;
+            static_for<k + 1, m>([&](auto I_) {
+                constexpr int i = decltype(I_)::value;
+                double v = gram<i, k>();
+#pragma unroll
+                for (int j = 0; j < k; j++) v = fma(-L.get(low(i, j)), L.get(low(k, j)), v);
+                L.set(low(i, k), v * r);
             });
-            const double a = ax.get(i), b = ay.get(i);
-            double dj = fma(a, a, b * b) + d(i);                                   // 1/2 |g_i|^2 = |a_i|^2
-#pragma unroll
-            for (int k = 0; k < i; k++) dj = fma(-row[k], row[k], dj);
-            invd[i] = fast_rsqrt(dj);
-#pragma unroll
-            for (int k = 0; k < i; k++) L.set(low(i, k), row[k]);
         });
     }
     // b := (L L')^-1 b
@@ -168,8 +168,15 @@ struct QpDual {
                     hh = fma(hc, hc, hh);
                 }
         }
+        {
+            double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-        for (int a = 0; a < n; a++) { const double qa = q.get(a); qq = fma(qa, qa, qq); }
+            for (int a = 0; a < n; a += 2) {
+                const double qa = q.get(a), qb = q.get(a + 1);
+                q0 = fma(qa, qa, q0); q1 = fma(qb, qb, q1);
+            }
+            qq = q0 + q1;
+        }
         // (feastol * max(1, |q|))^2 and (feastol * max(1, |h|))^2
         const double feas_x2 = 1e-4 * dmax(qq, 1.0), feas_z2 = 1e-4 * dmax(hh, 1.0);
 
@@ -210,25 +217,29 @@ struct QpDual {
         int iters = 0;
         for (; iters <= 50; iters++) {
             double rx[n];
-            double xq = 0.0, xrx = 0.0;
+            // the sums of this block are accumulated in two halves each (even / odd terms): half the dependent depth
+            double xq = 0.0, xrx = 0.0, xq1 = 0.0, xrx1 = 0.0;
 #pragma unroll
-            for (int a = 0; a < n; a++) {
-                const double xa = x.get(a), qa = q.get(a);
+            for (int a = 0; a < n; a += 2) {
+                const double xa = x.get(a), qa = q.get(a), xb = x.get(a + 1), qb = q.get(a + 1);
                 rx[a] = fma(2.0, xa, qa);
-                xrx = fma(xa, rx[a], xrx);
-                xq = fma(xa, qa, xq);
+                rx[a + 1] = fma(2.0, xb, qb);
+                xrx = fma(xa, rx[a], xrx); xrx1 = fma(xb, rx[a + 1], xrx1);
+                xq = fma(xa, qa, xq); xq1 = fma(xb, qb, xq1);
             }
-            const double f0 = 0.5 * (xrx + xq);
+            const double f0 = 0.5 * ((xrx + xrx1) + (xq + xq1));
             GT_acc([&](int c) { return z.get(c); }, rx);
-            double resx = 0.0, resz = 0.0, zrz = 0.0;
+            double resx = 0.0, resx1 = 0.0, resz = 0.0, resz1 = 0.0, zrz = 0.0, zrz1 = 0.0;
 #pragma unroll
-            for (int a = 0; a < n; a++) resx = fma(rx[a], rx[a], resx);
+            for (int a = 0; a < n; a += 2) { resx = fma(rx[a], rx[a], resx); resx1 = fma(rx[a + 1], rx[a + 1], resx1); }
+            resx += resx1;
             G_mul([&](int a) { return x.get(a); }, [&](int c, double g) {
                 const double r = g + (s.get(c) - h.get(c));
                 rz.set(c, r);
-                resz = fma(r, r, resz);
-                zrz = fma(z.get(c), r, zrz);
+                if (c & 1) { resz1 = fma(r, r, resz1); zrz1 = fma(z.get(c), r, zrz1); }
+                else { resz = fma(r, r, resz); zrz = fma(z.get(c), r, zrz); }
             });
+            resz += resz1; zrz += zrz1;
             const double pcost = f0, dcost = f0 + zrz - gap;
             // cvxopt's stopping rule without sqrt / division: relgap <= reltol  <=>  gap <= 1e-2 * denominator,
             // pres = sqrt(resz)/resz0 <= feastol  <=>  resz <= (1e-2 * resz0)^2   (equal up to 1 ulp at the threshold)
@@ -252,16 +263,19 @@ struct QpDual {
 #pragma unroll
             for (int c = 0; c < m; c++) dz[c] = t2.get(c);
             solve(dz);
-            double dsdz = 0.0, tmax = 0.0;
+            double dsdz = 0.0, dsdz1 = 0.0, tmax;
+            double cand[m];
 #pragma unroll
             for (int c = 0; c < m; c++) {
                 const double sc = s.get(c);
                 const double dsc = -sc - dd.get(c) * dz[c];
                 const double p = dsc * dz[c];
-                dsdz += p;
-                tmax = dmax(dmax(-dsc * inv_s(c), -dz[c] * inv_z(c)), tmax);
+                if (c & 1) dsdz1 += p; else dsdz += p;
+                cand[c] = dmax(-dsc * inv_s(c), -dz[c] * inv_z(c));
                 pp.set(c, p);                                  // keep only the Mehrotra correction term
             }
+            dsdz += dsdz1;
+            tmax = dmax(tree_max(cand), 0.0);
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);          // t == 0 ? 1 : min(1, 1/t)
             const double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
@@ -273,12 +287,12 @@ struct QpDual {
                 dz[c] = t2.get(c) + cr;
             }
             solve(dz);
-            tmax = 0.0;
 #pragma unroll
             for (int c = 0; c < m; c++) {
                 const double dsc = corr.get(c) - s.get(c) - dd.get(c) * dz[c];
-                tmax = dmax(dmax(-dsc * inv_s(c), -dz[c] * inv_z(c)), tmax);
+                cand[c] = dmax(-dsc * inv_s(c), -dz[c] * inv_z(c));
             }
+            tmax = dmax(tree_max(cand), 0.0);
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);          // t == 0 ? 1 : min(1, 0.99/t)
             // dx = -1/2 (rx + G'dz)
             double rx2[n];
@@ -289,14 +303,16 @@ struct QpDual {
 #pragma unroll
             for (int a = 0; a < n; a++) x.set(a, fma(hstep, rx2[a], x.get(a)));
             gap = 0.0;
+            double gap1 = 0.0;
 #pragma unroll
             for (int c = 0; c < m; c++) {
                 const double s0 = s.get(c);
                 const double dsc = corr.get(c) - s0 - dd.get(c) * dz[c];
                 const double sc = fma(step, dsc, s0), zc = fma(step, dz[c], z.get(c));
                 s.set(c, sc); z.set(c, zc);
-                gap = fma(sc, zc, gap);
+                if (c & 1) gap1 = fma(sc, zc, gap1); else gap = fma(sc, zc, gap);
             }
+            gap += gap1;
         }
 #pragma unroll
         for (int i = 0; i < N; i++) {

@@ -302,15 +302,17 @@ struct QpThread {
             }
             const double f0 = 0.5 * (xrx + xq);
             GT_acc([&](int c) { return z.get(c); }, rx);
-            double resx = 0.0, resz = 0.0, zrz = 0.0;
+            double resx = 0.0, resx1 = 0.0, resz = 0.0, resz1 = 0.0, zrz = 0.0, zrz1 = 0.0;      // sums in two halves
 #pragma unroll
-            for (int a = 0; a < n; a++) resx += rx[a] * rx[a];
+            for (int a = 0; a < n; a += 2) { resx = fma(rx[a], rx[a], resx); resx1 = fma(rx[a + 1], rx[a + 1], resx1); }
+            resx += resx1;
             G_mul(x, [&](int c, double gx) {
                 const double r = gx + (s.get(c) - h.get(c));
                 rz.set(c, r);
-                resz += r * r;
-                zrz += z.get(c) * r;
+                if (c & 1) { resz1 = fma(r, r, resz1); zrz1 = fma(z.get(c), r, zrz1); }
+                else { resz = fma(r, r, resz); zrz = fma(z.get(c), r, zrz); }
             });
+            resz += resz1; zrz += zrz1;
             const double pcost = f0, dcost = f0 + zrz - gap;
             bool gap_ok = gap <= 1e-7;
             if (pcost < 0.0) gap_ok = gap_ok || (gap <= -1e-2 * pcost);
@@ -332,20 +334,23 @@ struct QpThread {
             // corrector (rc = -s.z - ds_aff.dz_aff + sigma mu):  K dx = -rx - G'(w.rz - z + t2),  t2 = (rc + s.z)/s
             // (running one body twice under a runtime `pass` flag to halve the code was measured 2.5x slower)
             double dx[n];
-            double tmax = 0.0;
+            double tmax;
+            double cand[m];                                  // step-length candidates, reduced by a tree (common.cuh)
 #pragma unroll
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
             GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c); }, dx);
             solve(dx);
-            double dsdz = 0.0;
+            double dsdz = 0.0, dsdz1 = 0.0;
             G_mul(dx, [&](int c, double gd) {
                 const double dsc = -rz.get(c) - gd;
                 const double dzc = -z.get(c) - w.get(c) * dsc;
                 const double pr = dsc * dzc;                 // Mehrotra correction term
                 t2.set(c, pr);
-                dsdz += pr;
-                tmax = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tmax);
+                if (c & 1) dsdz1 += pr; else dsdz += pr;
+                cand[c] = dmax(-dsc * inv_s(c), -dzc * inv_z(c));
             });
+            dsdz += dsdz1;
+            tmax = dmax(tree_max(cand), 0.0);
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);
             double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
@@ -355,15 +360,16 @@ struct QpThread {
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
             GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c) - t2.get(c); }, dx);   // -(rc + z.rz)/s
             solve(dx);
-            tmax = 0.0;
             G_mul(dx, [&](int c, double gd) {
                 const double dsc = -rz.get(c) - gd;
                 const double dzc = fma(-w.get(c), dsc, t2.get(c) - z.get(c));                 // (rc - z.ds)/s
                 if (!MRB_QP_RECOMPUTE) { ds.set(c, dsc); dz.set(c, dzc); }
-                tmax = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tmax);
+                cand[c] = dmax(-dsc * inv_s(c), -dzc * inv_z(c));
             });
+            tmax = dmax(tree_max(cand), 0.0);
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);
             gap = 0.0;
+            double gap1 = 0.0;
             if (MRB_QP_RECOMPUTE) {
                 // the same expressions again; dx is laundered so that the compiler does not keep the first pass's
                 // 2m results live across the step-length reduction
@@ -375,8 +381,9 @@ struct QpThread {
                     const double dzc = fma(-w.get(c), dsc, t2.get(c) - zc0);
                     const double sc = fma(step, dsc, s.get(c)), zc = fma(step, dzc, zc0);
                     s.set(c, sc); z.set(c, zc);
-                    gap = fma(sc, zc, gap);
+                    if (c & 1) gap1 = fma(sc, zc, gap1); else gap = fma(sc, zc, gap);
                 });
+                gap += gap1;
             } else {
 #pragma unroll
                 for (int c = 0; c < m; c++) {
