@@ -67,7 +67,7 @@ void convert(const Params &p, int64_t count, Rows &r, const mrb_state_fields &f)
     auto F = [&](int row, int64_t e) -> double & { return sf[(size_t)row * count + e]; };
     auto I = [&](int row, int64_t e) -> int32_t & { return si[(size_t)row * count + e]; };
     auto cp = [&](auto &field, auto &row) { if (SET) row = (std::remove_reference_t<decltype(row)>)field; else field = (std::remove_reference_t<decltype(field)>)row; };
-    const int scf = 5 * N + 1, sci = 3;
+    const int scf = 5 * N + 1, sci = kCommonRowsI32;
     for (int64_t e = 0; e < count; e++) {
         if (f.poses)
             for (int k = 0; k < 3 * N; k++) cp(f.poses[e * 3 * N + k], F(k, e));
