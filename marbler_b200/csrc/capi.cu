@@ -115,10 +115,6 @@ extern "C" int mrb_create(const mrb_config *cfg, int device, int64_t num_envs, i
     e->p.obs_blocks = obs_block_count(c);
     e->p.rows_f64 = rows_f64(c);
     e->p.rows_i32 = rows_i32(c);
-    {
-        const char *ev = std::getenv("MRB_SORT_ENVS");
-        e->p.sort_envs = ev ? std::atoi(ev) != 0 : 1;
-    }
     e->p.collision_thr2 = thr2(c.collision_diameter);
     e->p.sense_thr2 = thr2(c.predator_radius);
     e->p.capture_thr2 = thr2(c.capture_radius);
@@ -215,7 +211,6 @@ extern "C" int mrb_step(mrb_env *env, const int32_t *actions, void *stream)
     if ((uintptr_t)actions & 15) return fail(env, MRB_E_ARG, "mrb_step: actions must be 16-byte aligned");
     cudaError_t st = cudaSetDevice(env->device);
     if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
-    env->p.key_row ^= 1;                    // this step reads the sort keys the previous one wrote
     return step_range(env, actions, 0, env->p.B, (cudaStream_t)stream);
 }
 
@@ -283,7 +278,6 @@ extern "C" int mrb_step_host(mrb_env *env, const int32_t *actions_host, float *o
     if (st != cudaSuccess) return cuda_fail(env, st, "cudaSetDevice");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t B = env->p.B, N = env->p.cfg.num_robots;
-    env->p.key_row ^= 1;                    // one step, however many chunk launches it is cut into
     if (!env->actions_dev && (st = cudaMalloc(&env->actions_dev, sizeof(int32_t) * B * N)) != cudaSuccess)
         return cuda_fail(env, st, "cudaMalloc(actions staging)");
     if (!env->pipe_ready) {

@@ -41,8 +41,6 @@ struct Params {
     int32_t obs_dim;    // D
     int32_t obs_blocks; // neighbour blocks per agent incl. self (PCP / Warehouse)
     int32_t rows_f64, rows_i32;
-    int32_t sort_envs;  // 1: teams of up to 4 robots group their envs by last step's solver iterations (MRB_SORT_ENVS=0 turns it off)
-    int32_t key_row;    // which of the two solver_iters rows (0 / 1) this step READS; it writes the other one
     // exact squared thresholds: sqrt(d2) <= r  <=>  d2 <= thr2(r)   (computed on the host)
     double collision_thr2, sense_thr2, capture_thr2, zone1_thr2;
 };
@@ -50,9 +48,7 @@ struct Params {
 // ---- state rows (env index fastest).  f64 rows:
 //   [0,N) x | [N,2N) y | [2N,3N) theta | [3N,4N) prev x | [4N,5N) prev y | 5N: episode return |
 //   5N+1 ..: scenario rows (PCP prey x0,y0,x1,y1,...; Simple goal x,y)
-// i32 rows: 0 episode_steps | 1 prev_valid | 2 episode_count | 3, 4 solver_iters (interior-point iterations of the env's
-//   last step: the key the one-env-per-thread kernels sort their envs by, see sorted_env in step_thread.cuh; two rows,
-//   read / written alternately, because the CTAs that share a group read the keys at different times) | 5.. scenario rows
+// i32 rows: 0 episode_steps | 1 prev_valid | 2 episode_count | 3.. scenario rows
 //   PCP: sensed mask, captured mask | Warehouse: loaded mask |
 //   MaterialTransport: load[N], zone1, zone2, messages (2 bits each) |
 //   ArcticTransport: grid (6 words, 2 bits per cell, cell = row*12+col), goal_col, pixel_type (2 bits each), reached mask
@@ -71,7 +67,7 @@ __host__ __device__ inline int scenario_rows_i32(const mrb_config &c)
     }
 }
 __host__ __device__ inline int rows_f64(const mrb_config &c) { return 5 * c.num_robots + 1 + scenario_rows_f64(c); }
-constexpr int kCommonRowsI32 = 5;
+constexpr int kCommonRowsI32 = 3;
 __host__ __device__ inline int rows_i32(const mrb_config &c) { return kCommonRowsI32 + scenario_rows_i32(c); }
 
 // ---- Philox4x32-10 (Salmon et al. SC'11); key = seed, counter = (env id, episode, block)

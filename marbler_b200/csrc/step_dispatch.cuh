@@ -10,9 +10,7 @@ template <int SCN, int N>
 inline cudaError_t launch_thread(const Params &p, const int32_t *actions, cudaStream_t s)
 {
     constexpr int tpb = ThreadShape<N>::kThreads;
-    // whole 256-env groups for the kernels that sort their envs (four CTAs per group, see sorted_env)
-    constexpr int unit = kSortedEnvs<N> ? kSortGroup : tpb;
-    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + unit - 1) / unit) * (unit / tpb);
+    const unsigned grid = (unsigned)((p.env_hi - p.env_lo + tpb - 1) / tpb);
     constexpr size_t smem = QpStore<N>::kBytes;
     if (smem > 48 * 1024) {
         const cudaError_t attr = cudaFuncSetAttribute(step_thread_kernel<SCN, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -197,7 +197,6 @@ __device__ void reset_env(const Params &p, int64_t env)
     si[0] = 0;
     si[1 * S] = 0;
     si[2 * S] += 1;
-    si[(4 - p.key_row) * S] = 0;                   // next step's sort key (the row this step reads is left alone)
     for (int r = 3 * N; r < 5 * N + 1; r++) sf[r * S] = 0.0;       // prev pose, episode return
     int32_t *sci = si + kCommonRowsI32 * S;
     double *scf = sf + (5 * N + 1) * S;
@@ -254,86 +253,12 @@ __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *ma
         for (int k = 0; k < nd; k++) p.buf.obs_f64[env * nd + k] = 0.0;
 }
 
-// ---- which env a thread steps (teams of up to 4 robots)
-// A warp of the one-env-per-thread kernels iterates its interior-point loop until the SLOWEST of its 32 envs has
-// converged: measured 1.40x the iterations the envs need (PredatorCapturePrey; MRB_STAT_QP_ITERS_WARP / MRB_STAT_QP_ITERS).
-// An env's iteration count changes slowly from one step to the next, so the threads of a 256-env group (four 64-thread
-// CTAs; each of them sorts the group on its own, deterministically, and takes its quarter) pick up the envs in the
-// order of last step's count: warps of similar envs, 1.40 -> ~1.24.  State rows are then gathered inside a 2 KB
-// window per row instead of read with consecutive addresses; results per env do not depend on the lane that steps it.
-constexpr int kSortGroup = 256, kSortBins = 128;
-template <int TPB>
-__device__ __forceinline__ int64_t sorted_env(const Params &p)
-{
-    static_assert(TPB == 64, "two warps per CTA, four CTAs per group");
-    constexpr int PER = kSortGroup / TPB;
-    __shared__ int s_bin[kSortBins];
-    __shared__ int s_warp0;
-    __shared__ uint8_t s_perm[kSortGroup];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    // CTA -> (group, quarter): the hardest quarter of every group first, the easiest quarters last, so that the CTAs
-    // still running when the grid drains (1.73 waves at 65,536 envs) are the short ones
-    const int groups = gridDim.x / PER;
-    const int group = blockIdx.x % groups, quarter = PER - 1 - blockIdx.x / groups;
-    const int64_t g0 = p.env_lo + (int64_t)group * kSortGroup;
-    const int32_t *keys = p.buf.state_i32 + (3 + p.key_row) * p.B;
-    for (int b = t; b < kSortBins; b += TPB) s_bin[b] = 0;
-    int key[PER], rank[PER];
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-        const int64_t e = g0 + t + TPB * j;
-        int k = kSortBins - 1;                                                  // envs past the end sort last
-        if (e < p.env_hi) { k = keys[e]; k = k < 0 ? 0 : (k > kSortBins - 2 ? kSortBins - 2 : k); }
-        key[j] = k;
-    }
-    __syncthreads();
-    // stable rank inside a bin, in the order (j, warp, lane): the envs of equal key before me
-#pragma unroll
-    for (int j = 0; j < PER; j++)
-#pragma unroll
-        for (int ww = 0; ww < 2; ww++) {
-            if (w == ww) {
-                const unsigned same = __match_any_sync(0xffffffffu, key[j]);
-                rank[j] = s_bin[key[j]] + __popc(same & ((1u << lane) - 1u));
-                __syncwarp();
-                if (lane == __ffs(same) - 1) s_bin[key[j]] += __popc(same);
-            }
-            __syncthreads();
-        }
-    // exclusive scan of the bin counts (two bins per thread)
-    const int c0 = s_bin[2 * t], c1 = s_bin[2 * t + 1];
-    int incl = c0 + c1;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (t == 31) s_warp0 = incl;
-    __syncthreads();
-    const int base = incl - (c0 + c1) + (w ? s_warp0 : 0);
-    s_bin[2 * t] = base;
-    s_bin[2 * t + 1] = base + c0;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < PER; j++) s_perm[s_bin[key[j]] + rank[j]] = (uint8_t)(t + TPB * j);
-    __syncthreads();
-    return g0 + s_perm[quarter * TPB + t];
-}
-template <int N>
-constexpr bool kSortedEnvs = !ThreadShape<N>::kPrimal && ThreadShape<N>::kThreads == 64;
-
 // ---- the step
 template <int SCN, int N>
 __global__ void __launch_bounds__(ThreadShape<N>::kThreads, ThreadShape<N>::kMinBlocks)
 step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
-    int64_t env = p.env_lo + (int64_t)blockIdx.x * ThreadShape<N>::kThreads + threadIdx.x;
-    if constexpr (kSortedEnvs<N>) {
-        // (linear order when the kernel also stores into host memory: those stores are only coalesced - 512 B of
-        // rewards, 32 B of flags per warp - when a warp's envs are consecutive; that path is PCIe bound anyway)
-        const bool host_mirror = p.hout.obs || p.hout.reward || p.hout.done || p.hout.message;
-        if (p.sort_envs && !host_mirror) env = sorted_env<ThreadShape<N>::kThreads>(p);
-    }
+    const int64_t env = p.env_lo + (int64_t)blockIdx.x * ThreadShape<N>::kThreads + threadIdx.x;
     const unsigned warp_envs = __ballot_sync(0xffffffffu, env < p.env_hi);      // lanes of this warp that own an env
     if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
@@ -773,7 +698,6 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     }
     si[0] = steps;
     si[S] = 1;
-    si[(4 - p.key_row) * S] = n_it;               // next step's sort key
     float team = 0.f;
 #pragma unroll
     for (int i = 0; i < N; i++) {

@@ -698,7 +698,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     for (int o = 16; o > 0; o >>= 1) team += __shfl_xor_sync(kFull, team, o);
     double ep_return = 0.0;
     if (lane == 0) {
-        si[0] = steps; si[S] = 1; si[(4 - p.key_row) * S] = n_it;
+        si[0] = steps; si[S] = 1;
         p.buf.done[env] = done ? 1 : 0;
         p.buf.message[env] = (uint8_t)msg;
         if (p.hout.done) p.hout.done[env] = done ? 1 : 0;

@@ -8,12 +8,9 @@ of the row layout that the tests check that conversion against."""
 import numpy as np
 
 
-COMMON_I32 = 5      # episode_steps | prev_valid | episode_count | 2 x solver_iters (a scheduling hint of the kernels, not env state)
-
-
 def rows(scenario, N, P):
     f = 5 * N + 1 + {"PredatorCapturePrey": 2 * P, "Simple": 2}.get(scenario, 0)
-    i = COMMON_I32 + {"PredatorCapturePrey": 2, "Warehouse": 1, "MaterialTransport": N + 3, "ArcticTransport": 9}.get(scenario, 0)
+    i = 3 + {"PredatorCapturePrey": 2, "Warehouse": 1, "MaterialTransport": N + 3, "ArcticTransport": 9}.get(scenario, 0)
     return f, i
 
 
@@ -55,24 +52,23 @@ def pack(scenario, N, P, st, B):
     si[0] = get("episode_steps", (), np.int32) if "episode_steps" in st else 0
     si[1] = get("prev_valid", (), np.int32) if "prev_valid" in st else 0
     si[2] = get("episode_count", (), np.int32) if "episode_count" in st else 0
-    c = COMMON_I32
     if scenario == "PredatorCapturePrey":
         sf[5 * N + 1:] = get("prey_loc", (2 * P,), np.float64).T
-        si[c] = _mask(get("prey_sensed", (P,), np.int64))
-        si[c + 1] = _mask(get("prey_captured", (P,), np.int64))
+        si[3] = _mask(get("prey_sensed", (P,), np.int64))
+        si[4] = _mask(get("prey_captured", (P,), np.int64))
     elif scenario == "Warehouse":
-        si[c] = _mask(get("loaded", (N,), np.int64))
+        si[3] = _mask(get("loaded", (N,), np.int64))
     elif scenario == "MaterialTransport":
-        si[c:c + N] = get("load", (N,), np.int32).T
-        si[c + N:c + N + 2] = get("zone_load", (2,), np.int32).T
-        si[c + N + 2] = _pack2(get("messages", (4,), np.int64))
+        si[3:3 + N] = get("load", (N,), np.int32).T
+        si[3 + N:5 + N] = get("zone_load", (2,), np.int32).T
+        si[5 + N] = _pack2(get("messages", (4,), np.int64))
     elif scenario == "ArcticTransport":
         grid = get("grid", (96,), np.int64)
         for w in range(6):
-            si[c + w] = _pack2(grid[:, 16 * w:16 * w + 16])
-        si[c + 6] = get("goal_col", (), np.int32)
-        si[c + 7] = _pack2(get("pixel_type", (N,), np.int64))
-        si[c + 8] = _mask(get("reached_goal", (N,), np.int64))
+            si[3 + w] = _pack2(grid[:, 16 * w:16 * w + 16])
+        si[9] = get("goal_col", (), np.int32)
+        si[10] = _pack2(get("pixel_type", (N,), np.int64))
+        si[11] = _mask(get("reached_goal", (N,), np.int64))
     elif scenario == "Simple":
         sf[5 * N + 1:] = get("goal", (2,), np.float64).T
     return sf, si
@@ -86,22 +82,21 @@ def unpack(scenario, N, P, sf, si):
     st = {"poses": sf[0:3 * N].T.reshape(B, 3, N).copy(), "prev_pose": prev,
           "episode_return": sf[5 * N].copy(),
           "episode_steps": si[0].copy(), "prev_valid": si[1].copy(), "episode_count": si[2].copy()}
-    c = COMMON_I32
     if scenario == "PredatorCapturePrey":
         st["prey_loc"] = sf[5 * N + 1:].T.reshape(B, P, 2).copy()
-        st["prey_sensed"] = _unmask(si[c], P)
-        st["prey_captured"] = _unmask(si[c + 1], P)
+        st["prey_sensed"] = _unmask(si[3], P)
+        st["prey_captured"] = _unmask(si[4], P)
     elif scenario == "Warehouse":
-        st["loaded"] = _unmask(si[c], N)
+        st["loaded"] = _unmask(si[3], N)
     elif scenario == "MaterialTransport":
-        st["load"] = si[c:c + N].T.copy()
-        st["zone_load"] = si[c + N:c + N + 2].T.copy()
-        st["messages"] = _unpack2(si[c + N + 2], 4)
+        st["load"] = si[3:3 + N].T.copy()
+        st["zone_load"] = si[3 + N:5 + N].T.copy()
+        st["messages"] = _unpack2(si[5 + N], 4)
     elif scenario == "ArcticTransport":
-        st["grid"] = np.concatenate([_unpack2(si[c + w], 16) for w in range(6)], axis=1).reshape(B, 8, 12).astype(np.uint8)
-        st["goal_col"] = si[c + 6].copy()
-        st["pixel_type"] = _unpack2(si[c + 7], N)
-        st["reached_goal"] = _unmask(si[c + 8], N)
+        st["grid"] = np.concatenate([_unpack2(si[3 + w], 16) for w in range(6)], axis=1).reshape(B, 8, 12).astype(np.uint8)
+        st["goal_col"] = si[9].copy()
+        st["pixel_type"] = _unpack2(si[10], N)
+        st["reached_goal"] = _unmask(si[11], N)
     elif scenario == "Simple":
         st["goal"] = sf[5 * N + 1:].T.copy()
     return st
