@@ -169,8 +169,9 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4, label
                  "qp_iterations": stats["qp_iterations"], "qp_iterations_warp": stats["qp_iterations_warp"]})
     assert stats["substeps"] <= B * T * cfg["update_frequency"] and stats["qp_iterations_warp"] >= stats["qp_iterations"]
     assert n_stalled <= max(2, int(stall_frac * B * T)), n_stalled
-    assert n_loose <= max(2, int(1e-4 * B * T)), n_loose
-    assert n_tie <= max(4, int(5e-2 * B * T)), n_tie
+    # measured on the B200 (profiles/r02_lockstep_counts.jsonl): loose <= 1.2e-5, exact ties <= 4.3e-4 of env-steps
+    assert n_loose <= max(2, int(5e-5 * B * T)), n_loose
+    assert n_tie <= max(4, int(2e-3 * B * T)), n_tie
     assert abs(stats["episodes"] - n_done) <= n_stalled and stats["env_steps"] == B * T
     assert stats["collisions"] + stats["boundary_exits"] >= n_msg - n_stalled
     assert stats["qp_stalls"] <= 4 * max(n_stalled, 1)
@@ -181,7 +182,8 @@ def _lockstep(oracle_lib, scenario, B, T, overrides=None, stall_frac=1e-4, label
 def test_rollout_lockstep_with_oracle(oracle_lib, scenario, B):
     # MaterialTransport spawns every robot in ONE column (1 x 6 grid, heading 0), i.e. exactly the symmetric
     # layout of the limit cycle, so it sees far more of them than the other scenarios
-    _lockstep(oracle_lib, scenario, B, 40, stall_frac=5e-3 if scenario == "MaterialTransport" else 1e-4)
+    # measured shares of excluded env-steps: MaterialTransport 9.0e-4, ArcticTransport 8.5e-5, the others <= 1.2e-5
+    _lockstep(oracle_lib, scenario, B, 40, stall_frac={"MaterialTransport": 3e-3, "ArcticTransport": 3e-4}.get(scenario, 1e-4))
 
 
 TEAM_CASES = [
@@ -204,7 +206,7 @@ TEAM_CASES = [
 def test_other_team_sizes_and_options_lockstep(oracle_lib, scenario, overrides):
     """Team sizes / options the reference fixtures do not cover, against the C oracle (which is pinned to the
     reference for N = 4, 6, 20): every kernel dispatch path (thread N = 2..6, warp N = 7..32)."""
-    _lockstep(oracle_lib, scenario, 1024, 25, overrides=overrides, stall_frac=2e-2)
+    _lockstep(oracle_lib, scenario, 1024, 25, overrides=overrides, stall_frac=1e-3)      # measured: none in any of these
 
 
 PCP20 = dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)

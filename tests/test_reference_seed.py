@@ -18,9 +18,12 @@ def _budget(ep, compared, lost):
     tolerances (1e-2) is a discontinuity: when a residual sits within rounding of its threshold two
     implementations stop one iteration apart and the returned velocities differ by ~1e-3, after which the
     trajectories separate for the rest of that episode.  That may happen at most once per fixture (150 steps,
-    ~300 solves) and at least 80 % of all steps must have been compared in sync."""
+    ~300 solves) and at least 90 % of all steps must have been compared in sync.  Measured (C oracle and CUDA path
+    alike): nine of the ten fixtures are followed for all 150 steps, MaterialTransport_seed11 loses the last 10 steps
+    of one episode."""
+    print("episode sync: %d of %d steps compared, %d loss(es) of sync" % (compared, ep.T, lost))
     assert lost <= 1, lost
-    assert compared >= 0.8 * ep.T, (compared, ep.T)
+    assert compared >= 0.9 * ep.T, (compared, ep.T)
 
 
 def _same_state(a, b, env_axis=None):
