@@ -335,22 +335,25 @@ struct QpThread {
             // (running one body twice under a runtime `pass` flag to halve the code was measured 2.5x slower)
             double dx[n];
             double tmax;
-            double cand[m];                                  // step-length candidates, reduced by a tree (common.cuh)
+            // step-length maximum over the 2m candidates in four interleaved running maxima (depth m/4 + 2 instead of a
+            // serial chain of 2m; a full pairwise tree would keep m candidates live, which this kernel has no registers for)
+            double tm[4];
 #pragma unroll
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
             GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c); }, dx);
             solve(dx);
             double dsdz = 0.0, dsdz1 = 0.0;
+            tm[0] = tm[1] = tm[2] = tm[3] = 0.0;
             G_mul(dx, [&](int c, double gd) {
                 const double dsc = -rz.get(c) - gd;
                 const double dzc = -z.get(c) - w.get(c) * dsc;
                 const double pr = dsc * dzc;                 // Mehrotra correction term
                 t2.set(c, pr);
                 if (c & 1) dsdz1 += pr; else dsdz += pr;
-                cand[c] = dmax(-dsc * inv_s(c), -dzc * inv_z(c));
+                tm[c & 3] = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tm[c & 3]);
             });
             dsdz += dsdz1;
-            tmax = dmax(tree_max(cand), 0.0);
+            tmax = dmax(dmax(tm[0], tm[1]), dmax(tm[2], tm[3]));
             double step = tmax <= 1.0 ? 1.0 : fast_rcp(tmax);
             double sg = dmin(dmax(1.0 - step + dsdz * fast_rcp(gap) * (step * step), 0.0), 1.0);
             const double sigmamu = sg * sg * sg * (gap / m);
@@ -360,13 +363,14 @@ struct QpThread {
             for (int a = 0; a < n; a++) dx[a] = -rx[a];
             GT_acc([&](int c) { return z.get(c) - w.get(c) * rz.get(c) - t2.get(c); }, dx);   // -(rc + z.rz)/s
             solve(dx);
+            tm[0] = tm[1] = tm[2] = tm[3] = 0.0;
             G_mul(dx, [&](int c, double gd) {
                 const double dsc = -rz.get(c) - gd;
                 const double dzc = fma(-w.get(c), dsc, t2.get(c) - z.get(c));                 // (rc - z.ds)/s
                 if (!MRB_QP_RECOMPUTE) { ds.set(c, dsc); dz.set(c, dzc); }
-                cand[c] = dmax(-dsc * inv_s(c), -dzc * inv_z(c));
+                tm[c & 3] = dmax(dmax(-dsc * inv_s(c), -dzc * inv_z(c)), tm[c & 3]);
             });
-            tmax = dmax(tree_max(cand), 0.0);
+            tmax = dmax(dmax(tm[0], tm[1]), dmax(tm[2], tm[3]));
             step = tmax <= 0.99 ? 1.0 : 0.99 * fast_rcp(tmax);
             gap = 0.0;
             double gap1 = 0.0;

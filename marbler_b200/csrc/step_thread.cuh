@@ -333,7 +333,31 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
                 }
                 ux[i] = dx; uy[i] = dy;
             }
+            // Teams of 5 and 6 robots: the solver alone needs more than the 255 registers (it spills inside its iteration
+            // loop even as a stand-alone kernel), and whatever else is live across the call makes that worse - measured
+            // 205 local loads + 117 stores per iteration here against 110 + 69 alone.  So everything that is only needed
+            // AFTER the solve is parked in local memory by hand (one store and one load per value and controller
+            // evaluation); volatile, so that the compiler cannot keep register copies alive across the solve.
+            constexpr bool kPark = ThreadShape<N>::kPrimal;
+            volatile double park[kPark ? 8 * N : 1];
+            volatile int park_act[kPark ? N : 1];
+            if constexpr (kPark) {
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    park[i] = px[i]; park[N + i] = py[i]; park[2 * N + i] = th[i]; park[3 * N + i] = gx[i];
+                    park[4 * N + i] = gy[i]; park[5 * N + i] = dist[i]; park[6 * N + i] = cs[i]; park[7 * N + i] = sn[i];
+                    park_act[i] = act[i];
+                }
+            }
             const int it = qp_run<N>(xix, xiy, ux, uy, c.barrier_default != 0, qp_store);   // controller.py:23
+            if constexpr (kPark) {
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    px[i] = park[i]; py[i] = park[N + i]; th[i] = park[2 * N + i]; gx[i] = park[3 * N + i];
+                    gy[i] = park[4 * N + i]; dist[i] = park[5 * N + i]; cs[i] = park[6 * N + i]; sn[i] = park[7 * N + i];
+                    act[i] = park_act[i];
+                }
+            }
             n_it += it;
             n_stall += it >= 25;
             n_qp++;
