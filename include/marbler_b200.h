@@ -208,9 +208,9 @@ const char *mrb_policy_last_error(const mrb_policy *policy);
 int mrb_policy_act(mrb_policy *policy, int64_t num_envs, const float *obs, float *hidden, int32_t *actions,
                    float *q, const uint8_t *fresh, void *cuda_stream);
 
-/* FP64 roofline denominator, measured: runs a kernel of independent DFMA chains (16 per thread, 148 x 8 CTAs of
- * 256 threads) for about `milliseconds` on `device`, timed with CUDA events, and returns the sustained rate in
- * TFLOP/s (2 flops per DFMA).  The env step is bound by FP64 issue, not by HBM, so bench.py
+/* FP64 roofline denominator, measured: runs a kernel of independent DFMA chains (8 per thread, one 1,024-thread
+ * CTA per SM) for about `milliseconds` on `device`, timed with CUDA events, and returns the rate of the best launch
+ * in TFLOP/s (2 flops per DFMA).  The env step is bound by FP64 issue, not by HBM, so bench.py
  * reports the step kernels' FP64 flop rate against this number. */
 int mrb_fp64_peak(int device, double milliseconds, double *tflops);
 

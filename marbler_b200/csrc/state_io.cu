@@ -142,19 +142,21 @@ void convert(const Params &p, int64_t count, Rows &r, const mrb_state_fields &f)
     }
 }
 
-// independent DFMA chains: 16 accumulators per thread, nothing else in the loop
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters, double a, double b)
+// independent DFMA chains: 8 accumulators per thread, 32 warps per SM, nothing else in the loop (the configuration of
+// scripts/microbench/fp64_latency.cu that reaches 2.0 warp-DFMA per clock and SM)
+constexpr int kPeakChains = 8;
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double *sink, int iters, double a, double b)
 {
-    double acc[16];
+    double acc[kPeakChains];
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = (double)(threadIdx.x + k);
+    for (int k = 0; k < kPeakChains; k++) acc[k] = (double)(threadIdx.x + k);
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) acc[k] = fma(acc[k], a, b);
+        for (int k = 0; k < kPeakChains; k++) acc[k] = fma(acc[k], a, b);
     }
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) s += acc[k];
+    for (int k = 0; k < kPeakChains; k++) s += acc[k];
     if (s == 12345.678) sink[0] = s;             // never true: keeps the chains alive
 }
 
@@ -196,11 +198,12 @@ extern "C" int mrb_fp64_peak(int device, double milliseconds, double *tflops)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int grid = prop.multiProcessorCount * 8, tpb = 256;
+    const int grid = prop.multiProcessorCount, tpb = 1024;
     int iters = 4096;
     double best = 0.0, spent = 0.0;
-    // warm-up launch, then repeat until the time budget is used; the best launch is the sustained pipe rate
-    for (int rep = 0; rep < 64 && (rep < 3 || spent < milliseconds); rep++) {
+    // the first launches bring the clocks up (untimed in effect: the best launch counts), then repeat until the time
+    // budget is used; launches of a few ms, short enough not to run into the power cap: the burst rate of the pipe
+    for (int rep = 0; rep < 256 && (rep < 8 || spent < milliseconds); rep++) {
         cudaEventRecord(e0, 0);
         dfma_peak_kernel<<<grid, tpb>>>(sink, iters, 1.0000001, 1e-9);
         count_launch();
@@ -210,7 +213,7 @@ extern "C" int mrb_fp64_peak(int device, double milliseconds, double *tflops)
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0) {
             spent += ms;
-            const double tf = 2.0 * 16.0 * (double)iters * grid * tpb / (ms * 1e-3) / 1e12;
+            const double tf = 2.0 * kPeakChains * (double)iters * grid * tpb / (ms * 1e-3) / 1e12;
             if (tf > best) best = tf;
         }
         if (ms < 2.0f && iters < (1 << 20)) iters *= 2;         // launches of a few ms: launch overhead is negligible
