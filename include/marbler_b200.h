@@ -179,8 +179,8 @@ int mrb_barrier_qp(int device, int32_t num_robots, int32_t barrier_default, int6
  * host once per env step: q, h = model(obs, h); actions = argmax(q).  mrb_policy_act does that for every
  * agent of every env in one kernel: fc1 -> ReLU -> GRUCell (or Linear+ReLU when use_rnn == 0) -> fc2 ->
  * greedy argmax, tensor-core MMAs on FP16 operands with FP32 accumulation and FP32 gates (tcgen05 / TMEM for
- * hidden 128 + GRUCell with <= 8 actions, mma.sync otherwise), reading the env's obs buffer and writing the
- * actions buffer mrb_step consumes (no host round trip). */
+ * hidden 128 + GRUCell with <= 8 actions, mma.sync otherwise) - or, with desc.accurate, in float32 throughout -,
+ * reading the env's obs buffer and writing the actions buffer mrb_step consumes (no host round trip). */
 typedef struct mrb_policy_desc {
     int32_t struct_size;        /* sizeof(mrb_policy_desc): ABI check */
     int32_t obs_dim;            /* D: width of one agent's row in the obs buffer */
@@ -191,7 +191,9 @@ typedef struct mrb_policy_desc {
     int32_t obs_agent_id;       /* append the one-hot agent id to the observation */
     int32_t use_rnn;            /* 1: nn.GRUCell, 0: nn.Linear + ReLU (rnn_agent.py:11-14) */
     int32_t non_shared;         /* 1: one weight set per agent (RNNNSAgent), 0: one shared set */
-    int32_t reserved0;
+    int32_t accurate;           /* 1: float32 operands and accumulation like the reference (plain FMA kernel, ~10x the
+                                 * time): the greedy actions of a checkpoint are the reference's; 0: FP16 tensor-core
+                                 * operands (q within ~1e-3 |q|, about one near-tie decision in a thousand differs) */
 } mrb_policy_desc;
 typedef struct mrb_policy mrb_policy;
 /* weights: HOST float32, (non_shared ? n_agents : 1) sets back to back, each set in state_dict order and

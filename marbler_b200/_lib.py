@@ -64,7 +64,7 @@ class StateFields(C.Structure):
 
 class PolicyDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("struct_size", "obs_dim", "input_dim", "hidden_dim", "n_actions", "n_agents",
-                                         "obs_agent_id", "use_rnn", "non_shared", "reserved0")]
+                                         "obs_agent_id", "use_rnn", "non_shared", "accurate")]
 
 
 _lib = None

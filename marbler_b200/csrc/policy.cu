@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "policy_tc.cuh"
 #include "policy_tc2.cuh"
+#include "policy_f32.cuh"
 
 namespace mrb {
 
@@ -299,6 +300,8 @@ struct mrb_policy {
     int num_sms;
     PolicyParams p;
     size_t smem_bytes;
+    float *w32;                 // float32 path (policy_f32.cuh), only when desc.accurate
+    mrb::f32::Params32 p32;
     std::string err;
 };
 
@@ -405,7 +408,46 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
     std::memset(&tcp2, 0, sizeof(tcp2));
     const int dp = (Din + 15) & ~15;
     const size_t tc2_smem = mrb::tc2::smem_bytes(dp, A);
-    const bool use_tc2 = H == 128 && d.use_rnn && dp <= mrb::tc::kMaxKp1 && A <= mrb::tc2::kMaxA && mrb::tc2::ring_depth(dp, A) >= 2;
+    const bool use_tc2 = !d.accurate && H == 128 && d.use_rnn && dp <= mrb::tc::kMaxKp1 && A <= mrb::tc2::kMaxA && mrb::tc2::ring_depth(dp, A) >= 2;
+    // float32 path: transposed float32 copies of every matrix (policy_f32.cuh)
+    std::vector<float> img32;
+    mrb::f32::Params32 p32;
+    std::memset(&p32, 0, sizeof(p32));
+    if (d.accurate) {
+        const int64_t sf = mrb::f32::image_floats(H, Din, A, d.use_rnn != 0, &p32);
+        img32.assign((size_t)sf * sets, 0.f);
+        for (int sidx = 0; sidx < sets; sidx++) {
+            const float *w = weights + per_set * sidx;
+            const float *fc1w = w, *fc1b = fc1w + (size_t)H * Din, *rw = fc1b + H;
+            float *o = img32.data() + (size_t)sf * sidx;
+            for (int u = 0; u < H; u++)
+                for (int k = 0; k < Din; k++) o[(size_t)k * H + u] = fc1w[(size_t)u * Din + k];
+            std::memcpy(o + p32.off_b1, fc1b, sizeof(float) * H);
+            const float *fc2w;
+            if (d.use_rnn) {
+                const float *wih = rw, *whh = wih + (size_t)3 * H * H, *bih = whh + (size_t)3 * H * H, *bhh = bih + 3 * H;
+                for (int g = 0; g < 3; g++)
+                    for (int u = 0; u < H; u++)
+                        for (int k = 0; k < H; k++) {
+                            o[p32.off_wih + ((size_t)g * H + k) * H + u] = wih[((size_t)g * H + u) * H + k];
+                            o[p32.off_whh + ((size_t)g * H + k) * H + u] = whh[((size_t)g * H + u) * H + k];
+                        }
+                std::memcpy(o + p32.off_bias, bih, sizeof(float) * 3 * H);
+                std::memcpy(o + p32.off_bias + 3 * H, bhh, sizeof(float) * 3 * H);
+                fc2w = bhh + 3 * H;
+            } else {
+                const float *wl = rw, *bl = wl + (size_t)H * H;
+                for (int u = 0; u < H; u++)
+                    for (int k = 0; k < H; k++) o[p32.off_wih + (size_t)k * H + u] = wl[(size_t)u * H + k];
+                std::memcpy(o + p32.off_bias, bl, sizeof(float) * H);
+                fc2w = bl + H;
+            }
+            std::memcpy(o + p32.off_w2, fc2w, sizeof(float) * (size_t)A * H);
+            std::memcpy(o + p32.off_b2, fc2w + (size_t)A * H, sizeof(float) * A);
+        }
+        p32.set_floats = sf; p32.obs_dim = d.obs_dim; p32.input_dim = Din; p32.n_actions = A; p32.n_agents = N;
+        p32.obs_agent_id = d.obs_agent_id; p32.non_shared = d.non_shared;
+    }
     if (use_tc2) {
         const int headf = mrb::tc2::head_floats(dp, A);
         const int64_t setb = 4LL * headf + (int64_t)mrb::tc2::kSlabsPerTile * mrb::tc2::kHalfSlabBytes;
@@ -447,6 +489,8 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
     pol->tcp2 = tcp2;
     pol->tc2_smem = tc2_smem;
     pol->num_sms = 0;
+    pol->w32 = nullptr;
+    pol->p32 = p32;
     if ((st = cudaSetDevice(device)) != cudaSuccess || (st = cudaMalloc(&pol->wpack, img.size() * sizeof(float))) != cudaSuccess ||
         (st = cudaMemcpy(pol->wpack, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
         const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
@@ -466,6 +510,17 @@ extern "C" int mrb_policy_create(const mrb_policy_desc *desc, int device, const 
         }
         pol->tcp2.img = pol->tc2_img;
     }
+    if (d.accurate) {
+        if ((st = cudaMalloc(&pol->w32, img32.size() * sizeof(float))) != cudaSuccess ||
+            (st = cudaMemcpy(pol->w32, img32.data(), img32.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            const std::string msg = std::string("mrb_policy_create: ") + cudaGetErrorString(st);
+            if (pol->w32) cudaFree(pol->w32);
+            cudaFree(pol->wpack);
+            delete pol;
+            return pfail(nullptr, MRB_E_CUDA, msg);
+        }
+        pol->p32.w = pol->w32;
+    }
     PolicyParams &p = pol->p;
     p.wpack = pol->wpack; p.set_floats = set_floats; p.B = 0;
     p.obs_dim = d.obs_dim; p.input_dim = Din; p.n_actions = A; p.n_agents = N;
@@ -482,6 +537,7 @@ extern "C" int mrb_policy_destroy(mrb_policy *p)
     cudaSetDevice(p->device);
     if (p->wpack) cudaFree(p->wpack);
     if (p->tc2_img) cudaFree(p->tc2_img);
+    if (p->w32) cudaFree(p->w32);
     delete p;
     return MRB_OK;
 }
@@ -507,6 +563,25 @@ extern "C" int mrb_policy_act(mrb_policy *pol, int64_t num_envs, const float *ob
     PolicyParams p = pol->p;
     p.B = num_envs;
     cudaStream_t s = (cudaStream_t)stream;
+    if (pol->w32) {                         // float32 arithmetic (desc.accurate)
+        mrb::f32::Params32 fp = pol->p32;
+        fp.B = num_envs;
+        const int H = pol->d.hidden_dim;
+        const size_t smem = mrb::f32::smem_bytes(H, fp.input_dim, fp.n_actions);
+        const dim3 grid((unsigned)((num_envs + mrb::f32::kRows - 1) / mrb::f32::kRows), (unsigned)fp.n_agents);
+        auto launch32 = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, H, smem, s>>>(fp, obs, hidden, actions, q, fresh);
+            return cudaGetLastError();
+        };
+        const bool rnn32 = pol->d.use_rnn != 0;
+        if (H == 128) st = rnn32 ? launch32(mrb::f32::policy_act_f32_kernel<128, true>) : launch32(mrb::f32::policy_act_f32_kernel<128, false>);
+        else st = rnn32 ? launch32(mrb::f32::policy_act_f32_kernel<64, true>) : launch32(mrb::f32::policy_act_f32_kernel<64, false>);
+        if (st != cudaSuccess) return pfail(pol, MRB_E_CUDA, std::string("policy kernel launch: ") + cudaGetErrorString(st));
+        count_launch();
+        return MRB_OK;
+    }
     // MRB_POLICY_TC=0 forces the mma.sync kernel for models that the persistent tcgen05 kernel covers
     static const bool tc_off = [] { const char *e = std::getenv("MRB_POLICY_TC"); return e && e[0] == '0'; }();
     if (pol->tc2_img && !tc_off) {

@@ -49,7 +49,9 @@ def flatten_state_dict(state_dict, n_agents):
 class Policy(object):
     """Greedy (argmax-q) policy on the GPU.  obs_dim / n_agents describe the env's obs buffer [B, N, D]."""
 
-    def __init__(self, state_dict, n_agents, obs_dim, obs_agent_id=None, device=None):
+    def __init__(self, state_dict, n_agents, obs_dim, obs_agent_id=None, device=None, accurate=False):
+        """accurate=True: float32 arithmetic like the reference's own forward pass (csrc/policy_f32.cuh) - the greedy
+        actions of a checkpoint are then the reference's, at ~10x the time of the FP16 tensor-core kernels."""
         if not torch.cuda.is_available():
             raise RuntimeError("marbler_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -62,19 +64,20 @@ class Policy(object):
         self.n_agents, self.obs_dim, self.hidden_dim, self.n_actions = n_agents, obs_dim, f["hidden_dim"], f["n_actions"]
         self.obs_agent_id, self.use_rnn, self.non_shared = bool(obs_agent_id), f["use_rnn"], f["non_shared"]
         d = _lib.PolicyDesc(C.sizeof(_lib.PolicyDesc), obs_dim, f["input_dim"], f["hidden_dim"], f["n_actions"], n_agents,
-                            int(self.obs_agent_id), int(self.use_rnn), int(self.non_shared), 0)
+                            int(self.obs_agent_id), int(self.use_rnn), int(self.non_shared), int(bool(accurate)))
+        self.accurate = bool(accurate)
         self.handle = C.c_void_p()
         _lib.check_policy(self.lib.mrb_policy_create(C.byref(d), index, flat.ctypes.data_as(C.c_void_p), flat.size,
                                                      C.byref(self.handle)))
 
     @classmethod
-    def from_files(cls, weights_path, model_config_path, n_agents, obs_dim, device=None):
+    def from_files(cls, weights_path, model_config_path, n_agents, obs_dim, device=None, accurate=False):
         """The reference's own artefacts: a `.th` state_dict and the sacred model json next to it
         (scenarios/<S>/models/, loaded by utilities/misc.py:66-95 load_env_and_model)."""
         sd = torch.load(weights_path, map_location="cpu")
         with open(model_config_path) as fh:
             mc = json.load(fh)
-        return cls(sd, n_agents, obs_dim, obs_agent_id=bool(mc.get("obs_agent_id", False)), device=device)
+        return cls(sd, n_agents, obs_dim, obs_agent_id=bool(mc.get("obs_agent_id", False)), device=device, accurate=accurate)
 
     def __del__(self):
         try:

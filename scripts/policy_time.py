@@ -11,7 +11,7 @@ sd = {k[3:]: z[k] for k in z.files if k.startswith("sd.")}
 cfg = dict(gu.Golden("PredatorCapturePrey_rollout").cfg)
 B = 65536
 env = VecEnv("PredatorCapturePrey", cfg, num_envs=B, device="cuda:0", seed=0, auto_reset=True)
-pol = Policy(sd, 4, 16, device="cuda:0")
+pol = Policy(sd, 4, 16, device="cuda:0", accurate="accurate" in sys.argv[1:])
 ro = Rollout(env, pol, use_graph=True, steps_per_graph=16)
 ro.reset()
 ro.run(40)
