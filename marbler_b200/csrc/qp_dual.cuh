@@ -201,7 +201,7 @@ struct QpDual {
             ts = dmax(zc, ts);
             tz = dmax(-zc, tz);
         });
-        const double nrm = dmax(sqrt(ss), 1.0);
+        const double nrm = ss > 1.0 ? ss * fast_rsqrt(ss) : 1.0;          // max(|z|, 1)
         const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;
 #pragma unroll

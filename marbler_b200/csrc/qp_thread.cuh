@@ -275,7 +275,7 @@ struct QpThread {
             ts = dmax(zc, ts);                // max(-s) = max(z)
             tz = dmax(-zc, tz);
         });
-        const double nrm = dmax(sqrt(ss), 1.0);
+        const double nrm = ss > 1.0 ? ss * fast_rsqrt(ss) : 1.0;          // max(|z|, 1)
         const double s_shift = ts >= -1e-8 * nrm ? 1.0 + ts : 0.0, z_shift = tz >= -1e-8 * nrm ? 1.0 + tz : 0.0;
         const bool do_s = ts >= -1e-8 * nrm, do_z = tz >= -1e-8 * nrm;
         double gap = 0.0;

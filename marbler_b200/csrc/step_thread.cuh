@@ -163,20 +163,34 @@ struct ObsRow {
 };
 
 // ---- reset: <Scenario>.reset() + roboEnv.reset() (distributional parity)
-// N distinct cells of the spawn grid, uniformly, in order (rps generate_initial_conditions, App. A.5)
+// index of the r-th (0-based) set bit of m: five popcount steps instead of a scan over the cells (the reset path runs
+// with one active lane per warp inside the step kernel, so its cost is its dependent instruction count)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int r)
+{
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(m & ((1u << w) - 1u));
+        if (r >= c) { r -= c; m >>= w; pos += w; }
+    }
+    return pos;
+}
+// N distinct cells of the spawn grid, uniformly, in order (rps generate_initial_conditions, App. A.5): draw i takes the
+// r-th still-free cell in ascending order, r uniform in [0, cells - i)
 template <typename F>
 __device__ __forceinline__ void spawn_grid(const mrb_spawn &sp, Philox &g, F emit)
 {
-    uint64_t taken = 0;
     const int cells = sp.xr * sp.yr;
+    uint64_t freem = cells >= 64 ? ~0ull : ((1ull << cells) - 1ull);
+    // cell / yr for cell < 64 as a multiply-shift (exact for every yr in 1..64: checked exhaustively in tests/test_host_logic.py)
+    const uint32_t inv = (65536u + (uint32_t)sp.yr - 1u) / (uint32_t)sp.yr;
     for (int i = 0; i < sp.count; i++) {
-        int r = (int)g.below((uint32_t)(cells - i)), cell = 0;
-        for (; cell < cells; cell++) {
-            if ((taken >> cell) & 1) continue;
-            if (r-- == 0) break;
-        }
-        taken |= 1ull << cell;
-        const int ix = cell / sp.yr, iy = cell % sp.yr;
+        int r = (int)g.below((uint32_t)(cells - i));
+        const uint32_t lo = (uint32_t)freem, hi = (uint32_t)(freem >> 32);
+        const int nlo = __popc(lo);
+        const int cell = r < nlo ? nth_set_bit(lo, r) : 32 + nth_set_bit(hi, r - nlo);
+        freem &= ~(1ull << cell);
+        const int ix = (int)(((uint32_t)cell * inv) >> 16), iy = cell - ix * sp.yr;
         // explicit _rn ops: no FMA contraction, so the spawn poses are bit-identical to numpy's
         const double x = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn((double)ix, sp.spacing), sp.w2), sp.sx1), sp.sx2);
         const double y = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn((double)iy, sp.spacing), sp.h2), sp.sy1), sp.sy2);
@@ -189,18 +203,20 @@ __device__ __forceinline__ void spawn_grid(const mrb_spawn &sp, Philox &g, F emi
     }
 }
 
+// `episode`: the env's episode counter (state_i32 row 2), read by the caller - the step kernels fetch it while their
+// write-back is in flight instead of stalling on it here
 template <int SCN>
-__device__ void reset_env(const Params &p, int64_t env)
+__device__ void reset_env(const Params &p, int64_t env, int32_t episode)
 {
     const mrb_config &c = p.cfg;
     const int N = c.num_robots;
     const int64_t S = p.B;
     double *sf = p.buf.state_f64 + env;
     int32_t *si = p.buf.state_i32 + env;
-    Philox g(p.seed, (uint64_t)(p.env_id0 + env), (uint32_t)si[2 * S]);
+    Philox g(p.seed, (uint64_t)(p.env_id0 + env), (uint32_t)episode);
     si[0] = 0;
     si[1 * S] = 0;
-    si[2 * S] += 1;
+    si[2 * S] = episode + 1;
     for (int r = 3 * N; r < 5 * N + 1; r++) sf[r * S] = 0.0;       // prev pose, episode return
     int32_t *sci = si + kCommonRowsI32 * S;
     double *scf = sf + (5 * N + 1) * S;
@@ -248,7 +264,7 @@ __global__ void reset_kernel(const __grid_constant__ Params p, const uint8_t *ma
     const int64_t env = p.env_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.env_hi) return;
     if (mask && !mask[env]) return;
-    reset_env<SCN>(p, env);
+    reset_env<SCN>(p, env, p.buf.state_i32[env + 2 * p.B]);
     // the reference returns an all-zero observation from reset (e.g. PredatorCapturePrey.py:136)
     const int nd = p.cfg.num_robots * p.obs_dim;
     float *o = p.buf.obs + env * nd;
@@ -292,6 +308,12 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     }
     const int steps = si[0] + 1;                  // episode_steps += 1: first line of every step()
     const bool prev_valid = si[S] != 0;
+    // PredatorCapturePrey: the prey positions are fetched now, with the rest of the state, into a thread-private array;
+    // loading them inside the tail's loop over the prey put one global round trip per prey on the critical path
+    double prey_xy[SCN == MRB_PCP ? 2 * MRB_MAX_PREY : 1];
+    if (SCN == MRB_PCP) {
+        for (int q = 0; q < 2 * c.num_prey; q++) prey_xy[q] = scf[q * S];
+    }
     int at_pix = 0, at_reached = 0;
     if (SCN == MRB_ARCTIC) { at_pix = sci[7 * S]; at_reached = sci[8 * S]; }
 
@@ -310,8 +332,8 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     if (c.track_dist && prev_valid) {             // roboEnv.py:55-56 at sub-step 0
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double dx = px[i] - qx[i], dy = py[i] - qy[i];
-            dist[i] = sqrt(dx * dx + dy * dy);
+            const double dx = px[i] - qx[i], dy = py[i] - qy[i], n2 = dx * dx + dy * dy;
+            dist[i] = n2 > 1e-200 ? n2 * fast_rsqrt(n2) : 0.0;             // |pose - previous pose|
         }
     }
     int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_itw = 0;
@@ -326,13 +348,13 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             double xix[N], xiy[N], ux[N], uy[N];
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                sincos(th[i], &sn[i], &cs[i]);
+                heading_sincos(th[i], sn[i], cs[i]);
                 xix[i] = px[i] + kProjectionDistance * cs[i];              // uni_to_si_states (A.7)
                 xiy[i] = py[i] + kProjectionDistance * sn[i];
                 double dx = gx[i] - xix[i], dy = gy[i] - xiy[i];           // si_position_controller (A.6)
-                const double nrm = sqrt(dx * dx + dy * dy);
-                if (nrm > kSiVelocityLimit) {
-                    const double sc = kSiVelocityLimit / nrm;
+                const double n2 = dx * dx + dy * dy;
+                if (n2 > kSiVelocityLimit * kSiVelocityLimit) {              // |dxi| > 0.15: scale to 0.15 (no sqrt, no division)
+                    const double sc = kSiVelocityLimit * fast_rsqrt(n2);
                     dx *= sc; dy *= sc;
                 }
                 ux[i] = dx; uy[i] = dy;
@@ -462,7 +484,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         for (int a = 0; a < N; a++) { bd[a] = -1.0; bx[a] = -5.0; by[a] = -5.0; }
         for (int q = 0; q < P; q++) {
             if ((captured >> q) & 1) continue;
-            const double qxp = scf[(2 * q) * S], qyp = scf[(2 * q + 1) * S];
+            const double qxp = prey_xy[2 * q], qyp = prey_xy[2 * q + 1];
             double d2[N];
             bool sense = false, capture = false;
 #pragma unroll
@@ -719,6 +741,9 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
     }
 
     // ---------------------------------------------------------------- write back
+    // the two loads of the tail are issued before the stores, so that their latency runs under them
+    const double ep_prev = sf[(5 * N) * S];
+    const int32_t episode = c.auto_reset ? si[2 * S] : 0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
         sf[i * S] = px[i]; sf[(N + i) * S] = py[i]; sf[(2 * N + i) * S] = th[i];
@@ -764,7 +789,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
         if (p.hout.done) p.hout.done[env] = done ? 1 : 0;
         if (p.hout.message) p.hout.message[env] = (uint8_t)msg;
     }
-    const double ep_return = sf[(5 * N) * S] + (double)team;
+    const double ep_return = ep_prev + (double)team;
     sf[(5 * N) * S] = ep_return;
 
     if (c.collect_stats && p.buf.stats) {
@@ -791,7 +816,7 @@ step_thread_kernel(const __grid_constant__ Params p, const int32_t *__restrict__
             atomicAdd(st + MRB_STAT_SCENARIO, (double)scen_metric);
         }
     }
-    if (done && c.auto_reset) reset_env<SCN>(p, env);
+    if (done && c.auto_reset) reset_env<SCN>(p, env, episode);
 }
 
 }  // namespace mrb

@@ -281,7 +281,7 @@ struct QpWarp {
                 tz = dmax(-z[k], tz);
             } else { s[k] = 1.0; z[k] = 1.0; }
         ss = warp_sum(ss); ts = warp_max(ts); tz = warp_max(tz);
-        const double nrm = dmax(sqrt(ss), 1.0);
+        const double nrm = ss > 1.0 ? ss * fast_rsqrt(ss) : 1.0;          // max(|z|, 1)
         double gap = 0.0;
 #pragma unroll
         for (int k = 0; k < PPL; k++)
@@ -451,7 +451,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         else if (a == 3) gy = fmin(py + stp, c.down);
     }
     double v = 0, om = 0, cs = 1, sn = 0, cd = 1, sd = 0, dist = 0;
-    if (c.track_dist && prev_valid && me) { const double dx = px - qx, dy = py - qy; dist = sqrt(dx * dx + dy * dy); }
+    if (c.track_dist && prev_valid && me) { const double dx = px - qx, dy = py - qy, n2 = dx * dx + dy * dy; dist = n2 > 1e-200 ? n2 * fast_rsqrt(n2) : 0.0; }
     int msg = 0, n_qp = 0, n_it = 0, n_stall = 0, n_sub = 0;
     const int UF = c.update_frequency;
     const double coff = c.collision_offset;
@@ -462,11 +462,11 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         if (k % c.ctrl_period == 0 || c.robotarium) {
             double xi_x = 0, xi_y = 0, ux = 0, uy = 0;
             if (me) {
-                sincos(th, &sn, &cs);
+                heading_sincos(th, sn, cs);
                 xi_x = px + kProjectionDistance * cs; xi_y = py + kProjectionDistance * sn;
                 double dx = gx - xi_x, dy = gy - xi_y;
-                const double nrm = sqrt(dx * dx + dy * dy);
-                if (nrm > kSiVelocityLimit) { const double sc = kSiVelocityLimit / nrm; dx *= sc; dy *= sc; }
+                const double n2 = dx * dx + dy * dy;
+                if (n2 > kSiVelocityLimit * kSiVelocityLimit) { const double sc = kSiVelocityLimit * fast_rsqrt(n2); dx *= sc; dy *= sc; }
                 ux = dx; uy = dy;
             }
             const int it = qp.run(xi_x, xi_y, ux, uy, c.barrier_default != 0);
@@ -477,7 +477,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
                 ww = clampd(ww, -kAngularLimit, kAngularLimit);
                 v = clampd(vv, -kMaxLinearVelocity, kMaxLinearVelocity);
                 om = clampd(ww, -kMaxAngularVelocity, kMaxAngularVelocity);
-                sincos(kTimeStep * om, &sd, &cd);
+                small_sincos(kTimeStep * om, sd, cd);
             }
         }
         bool viol = me && ((px < kArenaXMin) | (px > kArenaXMax) | (py < kArenaYMin) | (py > kArenaYMax));
@@ -726,7 +726,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         }
     }
     __syncwarp();
-    if (done && c.auto_reset && lane == 0) reset_env<SCN>(p, env);
+    if (done && c.auto_reset && lane == 0) reset_env<SCN>(p, env, si[2 * S]);
 }
 
 inline int pairs_per_lane(int N) { return (N * (N - 1) / 2 + 31) / 32; }

@@ -168,3 +168,12 @@ def test_stats_allreduce_two_ranks_gloo():
     for rank, vec, summ in res:
         assert vec[0] == 1001 and vec[1] == 2002 and vec[6] == 501
         assert summ["return_mean"] == 2.0 and summ["length_mean"] == 10.0
+
+
+def test_spawn_grid_division_trick_is_exact():
+    """csrc/step_thread.cuh spawn_grid: cell // yr as (cell * ceil(65536 / yr)) >> 16 for every grid the library accepts
+    (at most 64 cells)."""
+    for yr in range(1, 65):
+        inv = (65536 + yr - 1) // yr
+        for cell in range(64):
+            assert (cell * inv) >> 16 == cell // yr, (cell, yr)
