@@ -14,14 +14,14 @@ bench.py multiplies the live counters of the timed region with these coefficient
 
 # (scenario, robots) -> (a, b, c, d); fit residuals <= 0.6 % over 24 launches per kernel (profiles/r02_fp64_flop_model.json)
 COEFFICIENTS = {
-    ("PredatorCapturePrey", 4): (118.3, 1923.1, 879.0, 187.9),
-    ("Simple", 4): (118.2, 1923.5, 878.9, 88.0),
-    ("MaterialTransport", 4): (117.7, 1477.6, 937.3, 80.4),
-    ("ArcticTransport", 4): (116.0, 1230.8, 967.4, 124.8),
-    ("Warehouse", 6): (202.0, 2435.3, 3304.0, 198.0),
+    ("PredatorCapturePrey", 4): (96.3, 1656.8, 756.0, 220.5),
+    ("Simple", 4): (96.3, 1656.9, 822.0, 120.6),
+    ("MaterialTransport", 4): (95.8, 1292.9, 869.7, 114.5),
+    ("ArcticTransport", 4): (94.5, 1108.8, 892.4, 153.8),
+    ("Warehouse", 6): (176.0, 2309.2, 3114.6, 230.2),
     # one env per warp: the counts include the arithmetic every lane repeats (e.g. the diagonal-block factorisation is
     # run by all 32 lanes and one result is kept), i.e. executed rather than minimal flops
-    ("PredatorCapturePrey", 20): (1462.0, 67507.3, 84959.0, 22960.2),
+    ("PredatorCapturePrey", 20): (1465.4, 68580.1, 84837.2, 22824.4),
 }
 
 
