@@ -32,6 +32,16 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 __device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }   // a < b
+// FP64 tensor-core tile product D = A (8 x 4, row) * B (4 x 8, col) + C (8 x 8) = one DMMA.8x8x4 on sm_100a.  Lane
+// (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t + 1].  Measured on the B200
+// (scripts/microbench/dmma.cu, profiles/r02_dmma_microbench.txt): 26 cycles latency, 16 cycles of the FP64 pipe per
+// scheduler -- the flop rate of 8 warp-DFMAs at full lane use -- so it buys instruction slots and lane efficiency, not flops.
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 8 x 8 tiles (4 robots) per dimension that a team served by PPL pair slots per lane can have
+__host__ __device__ constexpr int max_tiles(int ppl) { return ppl <= 1 ? 2 : ppl <= 2 ? 3 : ppl <= 4 ? 4 : ppl <= 6 ? 5 : ppl <= 8 ? 6 : 8; }
 
 // Per-warp shared-memory workspace (doubles).  The Cholesky factor is stored as the lower triangle of
 // N x N blocks of 2 x 2 (block (i,k), k <= i, at 4 * (i (i + 1) / 2 + k): [xx, xy, yx, yy] = rows 2i, 2i+1 x
@@ -136,10 +146,50 @@ struct QpWarp {
                 o[0] = make_double2(x00, x01); o[1] = make_double2(x10, x11);
             }
         };
+        // Blocked factorisation.  A panel is four block columns (one 8 x 8 tile column).  Inside a panel the columns are
+        // finished left-looking by the lanes that own the block rows (the k loops below start at the panel); once a
+        // panel is complete its rank-8 contribution is subtracted from every trailing tile by the FP64 tensor cores
+        // (two DMMA.8x8x4 per tile, tiles read from and written back to the workspace): 40 DMMAs for 20 robots in place of
+        // 90 sweeps x 16 DFMAs that ran with 12 to 32 of 32 lanes idle.
+        const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;      // fragment coordinates
+        const int NT = (N + 3) >> 2;
+        auto panel_update = [&](int J) {
+            constexpr int TM = max_tiles(PPL);
+            // A fragments of the finished panel, rows of tile I2: lane holds L[8 I2 + g][8 J + 4 c + t], c = 0, 1
+            double af[TM][2];
+            int rowbase[TM];
+#pragma unroll
+            for (int I2 = 1; I2 < TM; I2++) {
+                const int i = 4 * I2 + fgh;
+                rowbase[I2] = 2 * i * (i + 1);
+                const bool ok = I2 > J && I2 < NT && i < N;
+                const double *src = Lb + rowbase[I2] + 16 * J + 4 * (ft >> 1) + 2 * fa + (ft & 1);
+                af[I2][0] = ok ? src[0] : 0.0;
+                af[I2][1] = ok ? src[8] : 0.0;
+            }
+#pragma unroll
+            for (int J2 = 1; J2 < TM; J2++) {
+                if (J2 <= J || J2 >= NT) continue;
+#pragma unroll
+                for (int I2 = 1; I2 < TM; I2++) {
+                    if (I2 < J2 || I2 >= NT) continue;
+                    const int i = 4 * I2 + fgh, k = 4 * J2 + ft;
+                    const bool ok = i < N && k <= i;
+                    double2 *cp = reinterpret_cast<double2 *>(Lb + rowbase[I2] + 4 * k + 2 * fa);
+                    double2 c = ok ? *cp : make_double2(0.0, 0.0);
+                    dmma_8x8x4(c.x, c.y, -af[I2][0], af[J2][0]);
+                    dmma_8x8x4(c.x, c.y, -af[I2][1], af[J2][1]);
+                    if (i == k && fa == 0) c.y = 0.0;       // the element above the diagonal of a diagonal block stays 0
+                    if (ok) *cp = c;
+                }
+            }
+            __syncwarp();
+        };
         int j = 0;
         // two block columns per sweep: one load of this lane's block (i,k) feeds the updates of S_ij and S_i,j+1
         // (16 FMAs per two lane-varying and four broadcast 128-bit loads instead of 8 per two and two)
         for (; j + 1 < N; j += 2) {
+            const int k0 = j & ~3;                          // first block column of this panel
             double axx = 1.0, axy = 0.0, ayx = 0.0, ayy = 1.0, bxx = 1.0, bxy = 0.0, byx = 0.0, byy = 1.0;
             if (me && lane >= j) {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
@@ -147,7 +197,7 @@ struct QpWarp {
                 const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
                 axx = a0.x; axy = a0.y; ayx = a1.x; ayy = a1.y;
                 if (lane > j) { const double2 b0 = ri[2 * j + 2], b1 = ri[2 * j + 3]; bxx = b0.x; bxy = b0.y; byx = b1.x; byy = b1.y; }
-                for (int k = 0; k < j; k++) {
+                for (int k = k0; k < j; k++) {
                     const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1], q0 = rj1[2 * k], q1 = rj1[2 * k + 1];
                     axx = fma(-i0.x, p0.x, axx); axx = fma(-i0.y, p0.y, axx);
                     axy = fma(-i0.x, p1.x, axy); axy = fma(-i0.y, p1.y, axy);
@@ -172,6 +222,7 @@ struct QpWarp {
             double y00, y01, y10, y11;
             finish_column(j + 1, bxx, bxy, byx, byy, y00, y01, y10, y11);
             __syncwarp();
+            if ((j & 3) == 2 && j + 2 < N) panel_update(j >> 2);
         }
         if (j < N) {                                        // odd team size: the last block column on its own
             double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
@@ -179,7 +230,7 @@ struct QpWarp {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
                 const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
                 sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
-                for (int k = 0; k < j; k++) {
+                for (int k = j & ~3; k < j; k++) {
                     const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1];
                     sxx = fma(-i0.x, p0.x, sxx); sxx = fma(-i0.y, p0.y, sxx);
                     sxy = fma(-i0.x, p1.x, sxy); sxy = fma(-i0.y, p1.y, sxy);
