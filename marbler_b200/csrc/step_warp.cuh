@@ -31,7 +31,6 @@ __device__ __forceinline__ double warp_max(double v)
     for (int o = 16; o > 0; o >>= 1) v = dmax(__shfl_xor_sync(kFull, v, o), v);
     return v;
 }
-__device__ __forceinline__ int pair_index(int a, int b, int N) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }   // a < b
 // FP64 tensor-core tile product D = A (8 x 4, row) * B (4 x 8, col) + C (8 x 8) = one DMMA.8x8x4 on sm_100a.  Lane
 // (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t + 1].  Measured on the B200
 // (scripts/microbench/dmma.cu, profiles/r02_dmma_microbench.txt): 26 cycles latency, 16 cycles of the FP64 pipe per
@@ -45,18 +44,29 @@ __host__ __device__ constexpr int max_tiles(int ppl) { return ppl <= 1 ? 2 : ppl
 
 // Per-warp shared-memory workspace (doubles).  The Cholesky factor is stored as the lower triangle of
 // N x N blocks of 2 x 2 (block (i,k), k <= i, at 4 * (i (i + 1) / 2 + k): [xx, xy, yx, yy] = rows 2i, 2i+1 x
-// columns 2k, 2k+1), 32-byte aligned so that a block is two 128-bit shared loads.
+// columns 2k, 2k+1), 32-byte aligned so that a block is two 128-bit shared loads.  Per-pair quantities that the robot
+// lanes sum over (w = z/s, right-hand sides, z) are kept as SYMMETRIC N x N matrices with an odd row stride: the lane
+// of robot i reads row i with constant offsets and no bank conflicts instead of gathering through the pair index
+// (1.6x the conflict-free wavefronts and five integer instructions per element before); the pair's owner writes both
+// mirror entries.  The pair directions a_ij = 2 (x_i - x_j) are not stored: they are differences of the doubled
+// positions (exact), read as broadcast 128-bit loads.
+__host__ __device__ inline int pair_row_stride(int N) { return N | 1; }
 __host__ __device__ inline size_t warp_workspace_doubles(int N)
 {
-    const size_t n = 2 * (size_t)N, m = (size_t)N * (N - 1) / 2;
-    const size_t d = 2 * (size_t)N * (N + 1) + 6 * n + 4 * (m > 0 ? m : 1);
-    return (d + 1) & ~(size_t)1;
+    const size_t n = 2 * (size_t)N;
+    const size_t d = 2 * (size_t)N * (N + 1) + 6 * n + 2 * (size_t)N * pair_row_stride(N);
+    return ((d + 1) & ~(size_t)1) + 64 * (((size_t)N + 3) / 4);          // + the inverses of the diagonal 8 x 8 tiles of L
 }
 
-template <int PPL>
+// NC: compile-time team size (0 = generic).  The tensor-core paths (DMMA panel updates of the factor, tile solves) are
+// compiled for NC != 0 only: with the team size known their tile loops and predicates fold away; with a run-time team
+// size the same code spills and is slower than the 2 x 2-block code it replaces (measured, 20 robots: 39.7 vs 28.5 ms).
+template <int PPL, int NC = 0>
 struct QpWarp {
+    static constexpr bool kTiles = NC != 0;
     int N, n, m, lane;
-    double *Lb, *invd, *vx, *vq, *vrx, *vdx, *xix, *xiy, *pax, *pay, *pw, *pz, *pt;
+    int NS;                                               // row stride of the pair matrices
+    double *Lb, *invd, *vx, *vq, *vrx, *vdx, *xi2, *Wm, *Ym, *Li;
     int pi[PPL], pj[PPL];
     bool pv[PPL];
     double h[PPL];
@@ -64,8 +74,10 @@ struct QpWarp {
     __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), lane(lane_)
     {
         Lb = ws; invd = Lb + 2 * (size_t)N * (N + 1); vx = invd + n; vq = vx + n; vrx = vq + n; vdx = vrx + n;
-        xix = vdx + n; xiy = xix + N; pax = xiy + N; pay = pax + m; pw = pay + m; pt = pw + m;
-        pz = pt;                                          // z and the right-hand-side multipliers are never live together
+        NS = pair_row_stride(N);
+        xi2 = vdx + n;                                    // (2 x_i, 2 y_i), interleaved
+        Wm = xi2 + n; Ym = Wm + (size_t)N * NS;           // Ym holds z or the right-hand-side multipliers (never live together)
+        Li = ws + (warp_workspace_doubles(N) - 64 * (((size_t)N + 3) / 4));      // dense row-major 8 x 8 per diagonal tile
 #pragma unroll
         for (int k = 0; k < PPL; k++) {                   // decode my pair slots once
             const int c = lane + 32 * k;
@@ -77,41 +89,50 @@ struct QpWarp {
     }
     __device__ __forceinline__ double *blk(int i, int k) const { return Lb + 4 * (size_t)(i * (i + 1) / 2 + k); }
 
-    // (G v)_c for my pair slots; the pair directions a_c are read back from the workspace (keeping them in
-    // registers as well costs 2 PPL doubles per lane, which is what caps the kernel at 8 warps per SM)
+    // (G v)_c for my pair slots; the pair directions a_c are recomputed from the doubled positions (keeping them in
+    // registers costs 2 PPL doubles per lane, which is what caps the kernel at 8 warps per SM)
     __device__ __forceinline__ void G_mul(const double *v, double (&out)[PPL]) const
     {
+        const double2 *v2 = reinterpret_cast<const double2 *>(v), *x2 = reinterpret_cast<const double2 *>(xi2);
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
-            const int c = pv[k] ? lane + 32 * k : 0;
-            out[k] = pv[k] ? pax[c] * (v[2 * pj[k]] - v[2 * pi[k]]) + pay[c] * (v[2 * pj[k] + 1] - v[2 * pi[k] + 1]) : 0.0;
+            const double2 xa = x2[pi[k]], xb = x2[pj[k]], va = v2[pi[k]], vb = v2[pj[k]];
+            out[k] = pv[k] ? (xa.x - xb.x) * (vb.x - va.x) + (xa.y - xb.y) * (vb.y - va.y) : 0.0;
         }
     }
-    // out (smem, robot lanes) += G' y, y in smem indexed by pair
+    // both mirror entries of a pair matrix
+    __device__ __forceinline__ void pair_store(double *M, int k, double v) const { M[pi[k] * NS + pj[k]] = v; M[pj[k] * NS + pi[k]] = v; }
+    __device__ __forceinline__ double pair_load(const double *M, int k) const { return M[pi[k] * NS + pj[k]]; }
+    // out (smem, robot lanes) += G' y, y a pair matrix: (G'y)_i = -sum_j a_ij y_ij with a_ij = 2 (x_i - x_j) seen from
+    // robot i (the diagonal entry of the matrix is 0 and a_ii = 0)
     __device__ __forceinline__ void GT_acc(const double *y, double *out) const
     {
         if (lane < N) {
+            const double2 *x2 = reinterpret_cast<const double2 *>(xi2);
+            const double2 me2 = x2[lane];
+            const double *row = y + lane * NS;
             double sx = 0.0, sy = 0.0;
             for (int j = 0; j < N; j++) {
-                if (j == lane) continue;
-                const int c = lane < j ? pair_index(lane, j, N) : pair_index(j, lane, N);
-                const double t = lane < j ? -y[c] : y[c];
-                sx += pax[c] * t; sy += pay[c] * t;
+                const double2 o = x2[j];
+                const double t = row[j];
+                sx = fma(me2.x - o.x, t, sx); sy = fma(me2.y - o.y, t, sy);
             }
-            out[2 * lane] += sx; out[2 * lane + 1] += sy;
+            out[2 * lane] -= sx; out[2 * lane + 1] -= sy;
         }
     }
-    // K := 2I + G' diag(pw) G, then in-place Cholesky by 2 x 2 blocks (left-looking; lane i owns block
+    // K := 2I + G' diag(w) G, then in-place Cholesky by 2 x 2 blocks (left-looking; lane i owns block
     // row i); invd = reciprocals of the diagonal of L
     __device__ void factor()
     {
         __syncwarp();
         if (lane < N) {
             double dxx = 2.0, dxy = 0.0, dyy = 2.0;
+            const double2 *x2 = reinterpret_cast<const double2 *>(xi2);
+            const double2 me2 = x2[lane];
+            const double *wrow = Wm + lane * NS;
             for (int j = 0; j < N; j++) {
-                if (j == lane) continue;
-                const int c = lane < j ? pair_index(lane, j, N) : pair_index(j, lane, N);
-                const double w = pw[c], a = pax[c], b = pay[c];
+                const double2 xo = x2[j];
+                const double w = wrow[j], a = me2.x - xo.x, b = me2.y - xo.y;    // w_ii = 0
                 const double wa = w * a, wb = w * b;
                 const double pxx = wa * a, pxy = wa * b, pyy = wb * b;
                 dxx += pxx; dxy += pxy; dyy += pyy;
@@ -189,7 +210,7 @@ struct QpWarp {
         // two block columns per sweep: one load of this lane's block (i,k) feeds the updates of S_ij and S_i,j+1
         // (16 FMAs per two lane-varying and four broadcast 128-bit loads instead of 8 per two and two)
         for (; j + 1 < N; j += 2) {
-            const int k0 = j & ~3;                          // first block column of this panel
+            const int k0 = kTiles ? (j & ~3) : 0;           // first block column of this panel
             double axx = 1.0, axy = 0.0, ayx = 0.0, ayy = 1.0, bxx = 1.0, bxy = 0.0, byx = 0.0, byy = 1.0;
             if (me && lane >= j) {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
@@ -222,7 +243,7 @@ struct QpWarp {
             double y00, y01, y10, y11;
             finish_column(j + 1, bxx, bxy, byx, byy, y00, y01, y10, y11);
             __syncwarp();
-            if ((j & 3) == 2 && j + 2 < N) panel_update(j >> 2);
+            if (kTiles && (j & 3) == 2 && j + 2 < N) panel_update(j >> 2);
         }
         if (j < N) {                                        // odd team size: the last block column on its own
             double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
@@ -230,7 +251,7 @@ struct QpWarp {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
                 const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
                 sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
-                for (int k = j & ~3; k < j; k++) {
+                for (int k = kTiles ? (j & ~3) : 0; k < j; k++) {
                     const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1];
                     sxx = fma(-i0.x, p0.x, sxx); sxx = fma(-i0.y, p0.y, sxx);
                     sxy = fma(-i0.x, p1.x, sxy); sxy = fma(-i0.y, p1.y, sxy);
@@ -242,9 +263,111 @@ struct QpWarp {
             finish_column(j, sxx, sxy, syx, syy, x00, x01, x10, x11);
             __syncwarp();
         }
+        // Inverses of the diagonal 8 x 8 tiles of L (the triangular solves below multiply by them instead of running
+        // four dependent 2 x 2 steps per tile): lane (T, c) = (lane / 8, lane % 8) solves L_TT x = e_c by forward
+        // substitution; four tiles per round.  Rows past the matrix (ragged last tile) give zeros.
+        for (int T0 = 0; kTiles && T0 < NT; T0 += 4) {
+            const int T = T0 + (lane >> 3), c = lane & 7;
+            const bool okT = T < NT;
+            const int Tc = okT ? T : 0;
+            const int nv = okT ? (n - 8 * Tc < 8 ? n - 8 * Tc : 8) : 0;     // rows of this tile inside the matrix
+            double x[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const bool okr = r < nv;
+                const int i = 4 * Tc + (r >> 1);
+                // row r of the tile: (L[r][2q], L[r][2q + 1]) = blk(i, 4T + q)[2 (r % 2) ..]
+                const double2 *row = reinterpret_cast<const double2 *>(Lb + 2 * i * (i + 1) + 16 * Tc + 2 * (r & 1));
+                double sum = r == c ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 0; 2 * q < r; q++) {
+                    const double2 l = okr ? row[2 * q] : make_double2(0.0, 0.0);
+                    sum = fma(-l.x, x[2 * q], sum);
+                    if (2 * q + 1 < r) sum = fma(-l.y, x[2 * q + 1], sum);
+                }
+                x[r] = okr ? sum * invd[8 * Tc + r] : 0.0;
+            }
+            if (okT) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) Li[64 * T + 8 * r + c] = x[r];
+            }
+        }
+        __syncwarp();
     }
-    // b (smem) := K^-1 b, forward and backward substitution by blocks; lane i carries (b_2i, b_2i+1)
+    // b (smem) := K^-1 b by 8 x 8 tiles on the FP64 tensor cores.  The vector lives in "row layout": lane (g, t) holds
+    // element 8 I + g of every tile I (the four lanes of a group hold copies), which is what a DMMA with the vector
+    // replicated over the eight columns of B returns in both accumulators.  Forward: y_I = inv(L_II) (b_I - sum_J<I
+    // L_IJ y_J); backward: x_I = inv(L_II)' (y_I - sum_J>I L_JI' x_J): five dependent tile steps each way for 20
+    // robots instead of twenty 2 x 2 steps with two shuffle broadcasts each.
     __device__ void solve(double *b) const
+    {
+        if constexpr (!kTiles) { solve_rows(b); return; }
+        __syncwarp();
+        constexpr int TM = max_tiles(PPL);
+        const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;
+        const int NT = (N + 3) >> 2;
+        const int s0 = 4 * ft, s1 = 16 + 4 * ft;            // lanes holding elements t and 4 + t of a tile in row layout
+        double acc[TM], nb[TM][2];
+        int rowbase[TM];
+#pragma unroll
+        for (int I = 0; I < TM; I++) {
+            const int i = 4 * I + fgh;
+            rowbase[I] = 2 * i * (i + 1);
+            acc[I] = (I < NT && 8 * I + fg < n) ? b[8 * I + fg] : 0.0;
+        }
+        // B fragments of a vector held in row layout: lane (g, t) needs elements 4 c + t, c = 0, 1
+        auto spread = [&](double v, double &b0, double &b1) { b0 = __shfl_sync(kFull, v, s0); b1 = __shfl_sync(kFull, v, s1); };
+#pragma unroll
+        for (int I = 0; I < TM; I++) {
+            if (I >= NT) continue;
+            double c0 = acc[I], c1 = c0;
+            const bool okr = 8 * I + fg < n;
+#pragma unroll
+            for (int J = 0; J < TM; J++) {
+                if (J >= I) continue;
+                // L[8 I + g][8 J + 4 c + t]
+                const double *src = Lb + rowbase[I] + 16 * J + 4 * (ft >> 1) + 2 * fa + (ft & 1);
+                dmma_8x8x4(c0, c1, okr ? src[0] : 0.0, nb[J][0]);
+                dmma_8x8x4(c0, c1, okr ? src[8] : 0.0, nb[J][1]);
+            }
+            double t0, t1, d0 = 0.0, d1 = 0.0;
+            spread(c0, t0, t1);
+            const double *inv = Li + 64 * I + 8 * fg + ft;
+            dmma_8x8x4(d0, d1, inv[0], t0);
+            dmma_8x8x4(d0, d1, inv[4], t1);
+            acc[I] = d0;
+            spread(-d0, nb[I][0], nb[I][1]);
+        }
+#pragma unroll
+        for (int I = TM - 1; I >= 0; I--) {
+            if (I >= NT) continue;
+            double c0 = acc[I], c1 = c0;
+#pragma unroll
+            for (int J = TM - 1; J >= 0; J--) {
+                if (J <= I || J >= NT) continue;
+                // (L_JI)'[g][4 c + t] = L[8 J + 4 c + t][8 I + g]
+                const int i0 = 4 * J + (ft >> 1), i1 = i0 + 2;
+                const int off = 16 * I + 4 * fgh + 2 * (ft & 1) + fa;
+                dmma_8x8x4(c0, c1, 8 * J + ft < n ? Lb[2 * i0 * (i0 + 1) + off] : 0.0, nb[J][0]);
+                dmma_8x8x4(c0, c1, 8 * J + 4 + ft < n ? Lb[2 * i1 * (i1 + 1) + off] : 0.0, nb[J][1]);
+            }
+            double t0, t1, d0 = 0.0, d1 = 0.0;
+            spread(c0, t0, t1);
+            const double *inv = Li + 64 * I + 8 * ft + fg;      // inv(L_II)'[g][4 c + t] = inv[4 c + t][g]
+            dmma_8x8x4(d0, d1, inv[0], t0);
+            dmma_8x8x4(d0, d1, inv[32], t1);
+            acc[I] = d0;
+            spread(-d0, nb[I][0], nb[I][1]);
+        }
+        if (ft == 0) {
+#pragma unroll
+            for (int I = 0; I < TM; I++)
+                if (I < NT && 8 * I + fg < n) b[8 * I + fg] = acc[I];
+        }
+        __syncwarp();
+    }
+    // the same by 2 x 2 blocks: lane i carries (b_2i, b_2i+1), N dependent steps each way (run-time team sizes)
+    __device__ void solve_rows(double *b) const
     {
         __syncwarp();
         const bool me = lane < N;
@@ -289,7 +412,8 @@ struct QpWarp {
         if (m == 0) return 0;
         __syncwarp();
         if (lane < N) {
-            xix[lane] = xi_x; xiy[lane] = xi_y;
+            xi2[2 * lane] = 2.0 * xi_x; xi2[2 * lane + 1] = 2.0 * xi_y;
+            Wm[lane * NS + lane] = 0.0; Ym[lane * NS + lane] = 0.0;
             vq[2 * lane] = -2.0 * ux; vq[2 * lane + 1] = -2.0 * uy;
         }
         __syncwarp();
@@ -299,12 +423,11 @@ struct QpWarp {
         for (int k = 0; k < PPL; k++) {
             h[k] = 0.0;
             if (pv[k]) {
-                const double ex = xix[pi[k]] - xix[pj[k]], ey = xiy[pi[k]] - xiy[pj[k]];
+                const double ex = 0.5 * (xi2[2 * pi[k]] - xi2[2 * pj[k]]), ey = 0.5 * (xi2[2 * pi[k] + 1] - xi2[2 * pj[k] + 1]);
                 const double hv = (ex * ex + ey * ey) - r2;
                 const double gain = barrier_default ? 100.0 : (hv >= 0.0 ? 100.0 : 1e6);
                 h[k] = gain * (hv * hv * hv);
-                const int c = lane + 32 * k;
-                pax[c] = 2.0 * ex; pay[c] = 2.0 * ey; pw[c] = 1.0; pt[c] = h[k];
+                pair_store(Wm, k, 1.0); pair_store(Ym, k, h[k]);
                 hh = fma(h[k], h[k], hh);
             }
         }
@@ -317,7 +440,7 @@ struct QpWarp {
         factor();
         if (lane < N) { vx[2 * lane] = -vq[2 * lane]; vx[2 * lane + 1] = -vq[2 * lane + 1]; }
         __syncwarp();
-        GT_acc(pt, vx);
+        GT_acc(Ym, vx);
         solve(vx);
         double s[PPL], z[PPL];
         G_mul(vx, z);
@@ -349,7 +472,7 @@ struct QpWarp {
             double xq = 0.0, xrx = 0.0;
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < PPL; k++) if (pv[k]) pz[lane + 32 * k] = z[k];
+            for (int k = 0; k < PPL; k++) if (pv[k]) pair_store(Ym, k, z[k]);
             if (lane < N) {
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
@@ -359,7 +482,7 @@ struct QpWarp {
                 }
             }
             __syncwarp();
-            GT_acc(pz, vrx);
+            GT_acc(Ym, vrx);
             double rz[PPL];
             G_mul(vx, rz);
             double resx = 0.0, resz = 0.0, zrz = 0.0;
@@ -383,19 +506,19 @@ struct QpWarp {
             // w = z/s is read back from the workspace and the corrector's (ds, dz) are recomputed in the update
             // pass: 6 PPL fewer live doubles per lane than storing them
             double t2[PPL], gv[PPL];
-            __syncwarp();                                   // every lane is done reading pz (= pt)
+            __syncwarp();                                   // every lane is done reading z from Ym
 #pragma unroll
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     const double w = z[k] * fast_rcp1(s[k]);
-                    pw[lane + 32 * k] = w;
-                    pt[lane + 32 * k] = z[k] - w * rz[k];
+                    pair_store(Wm, k, w);
+                    pair_store(Ym, k, z[k] - w * rz[k]);
                 }
             factor();
             // predictor
             if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
             __syncwarp();
-            GT_acc(pt, vdx);
+            GT_acc(Ym, vdx);
             solve(vdx);
             G_mul(vdx, gv);
             double dsdz = 0.0, tmax = 0.0;
@@ -403,7 +526,7 @@ struct QpWarp {
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     const double ds = -rz[k] - gv[k];
-                    const double dz = -z[k] - pw[lane + 32 * k] * ds;
+                    const double dz = -z[k] - pair_load(Wm, k) * ds;
                     t2[k] = ds * dz;
                     dsdz += t2[k];
                     tmax = dmax(dmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])), tmax);
@@ -418,11 +541,11 @@ struct QpWarp {
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     t2[k] = (sigmamu - t2[k]) * fast_rcp1(s[k]);
-                    pt[lane + 32 * k] = z[k] - pw[lane + 32 * k] * rz[k] - t2[k];
+                    pair_store(Ym, k, z[k] - pair_load(Wm, k) * rz[k] - t2[k]);
                 }
             if (lane < N) { vdx[2 * lane] = -vrx[2 * lane]; vdx[2 * lane + 1] = -vrx[2 * lane + 1]; }
             __syncwarp();
-            GT_acc(pt, vdx);
+            GT_acc(Ym, vdx);
             solve(vdx);
             G_mul(vdx, gv);
             tmax = 0.0;
@@ -430,7 +553,7 @@ struct QpWarp {
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     const double ds = -rz[k] - gv[k];
-                    const double dz = fma(-pw[lane + 32 * k], ds, t2[k] - z[k]);
+                    const double dz = fma(-pair_load(Wm, k), ds, t2[k] - z[k]);
                     tmax = dmax(dmax(-ds * fast_rcp1(s[k]), -dz * fast_rcp1(z[k])), tmax);
                 }
             tmax = warp_max(tmax);
@@ -441,7 +564,7 @@ struct QpWarp {
             for (int k = 0; k < PPL; k++)
                 if (pv[k]) {
                     const double ds = -rz[k] - gv[k];
-                    const double dz = fma(-pw[lane + 32 * k], ds, t2[k] - z[k]);
+                    const double dz = fma(-pair_load(Wm, k), ds, t2[k] - z[k]);
                     s[k] = fma(step, ds, s[k]);
                     z[k] = fma(step, dz, z[k]);
                     gap = fma(s[k], z[k], gap);
@@ -477,7 +600,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     int32_t *si = p.buf.state_i32 + env;
     int32_t *sci = si + kCommonRowsI32 * S;
     double *scf = sf + (5 * N + 1) * S;
-    QpWarp<PPL> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    QpWarp<PPL, NC> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
     const bool me = lane < N;
 
     double px = 0, py = 0, th = 0, qx = 0, qy = 0;
@@ -571,7 +694,7 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
 
     // stage every robot's position in the (now idle) QP workspace so that any lane can read any
     // robot without shuffles inside lane-dependent control flow
-    double *spx = qp.xix, *spy = qp.xiy, *sbx = qp.vx, *sby = qp.vq;
+    double *spx = qp.xi2, *spy = qp.xi2 + N, *sbx = qp.vx, *sby = qp.vq;
     __syncwarp();
     if (me) { spx[lane] = px; spy[lane] = py; }
     __syncwarp();
@@ -810,16 +933,17 @@ inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cud
 }
 
 // ---- barrier QP alone, one problem per warp
-template <int PPL>
+template <int PPL, int NC = 0>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MRB_WARP_MIN_BLOCKS)
-qp_warp_kernel(int N, int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
+qp_warp_kernel(int N_, int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
                double *__restrict__ u, int32_t *__restrict__ iters)
 {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (e >= B) return;
-    QpWarp<PPL> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    const int N = NC ? NC : N_;
+    QpWarp<PPL, NC> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
     double xx = 0, xy = 0, ux = 0, uy = 0;
     if (lane < N) { xx = xi[lane * B + e]; xy = xi[(N + lane) * B + e]; ux = dxi[lane * B + e]; uy = dxi[(N + lane) * B + e]; }
     const int it = qp.run(xx, xy, ux, uy, barrier_default != 0);
@@ -827,18 +951,19 @@ qp_warp_kernel(int N, int64_t B, int barrier_default, const double *__restrict__
     if (iters && lane == 0) iters[e] = it;
 }
 
-template <int PPL>
+template <int PPL, int NC = 0>
 inline cudaError_t launch_qp_warp_ppl(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
 {
     const size_t smem = warp_workspace_doubles(N) * sizeof(double) * kWarpsPerBlock;
-    cudaError_t st = cudaFuncSetAttribute(qp_warp_kernel<PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t st = cudaFuncSetAttribute(qp_warp_kernel<PPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
-    qp_warp_kernel<PPL><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem, s>>>(N, B, bd, dxi, xi, u, iters);
+    qp_warp_kernel<PPL, NC><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem, s>>>(N, B, bd, dxi, xi, u, iters);
     return cudaSuccess;
 }
 inline cudaError_t launch_qp_warp(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
 {
     const int ppl = pairs_per_lane(N);
+    if (N == 20 && !std::getenv("MRB_WARP_GENERIC")) return launch_qp_warp_ppl<6, 20>(N, bd, B, dxi, xi, u, iters, s);   // the tensor-core solver
     if (ppl <= 1) return launch_qp_warp_ppl<1>(N, bd, B, dxi, xi, u, iters, s);
     if (ppl <= 2) return launch_qp_warp_ppl<2>(N, bd, B, dxi, xi, u, iters, s);
     if (ppl <= 4) return launch_qp_warp_ppl<4>(N, bd, B, dxi, xi, u, iters, s);
