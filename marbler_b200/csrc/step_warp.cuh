@@ -120,9 +120,8 @@ struct QpWarp {
             out[2 * lane] -= sx; out[2 * lane + 1] -= sy;
         }
     }
-    // K := 2I + G' diag(w) G, then in-place Cholesky by 2 x 2 blocks (left-looking; lane i owns block
-    // row i); invd = reciprocals of the diagonal of L
-    __device__ void factor()
+    // K := 2I + G' diag(w) G as the lower triangle of 2 x 2 blocks (lane i builds block row i)
+    __device__ __forceinline__ void assemble()
     {
         __syncwarp();
         if (lane < N) {
@@ -145,10 +144,17 @@ struct QpWarp {
             o[0] = make_double2(dxx, 0.0); o[1] = make_double2(dxy, dyy);
         }
         __syncwarp();
+    }
+    // K -> its Cholesky factor, in place; invd = reciprocals of the diagonal of L
+    __device__ void factor()
+    {
+        assemble();
+        if constexpr (kTiles) { factor_tiles(); return; }
         const bool me = lane < N;
         const double2 *ri = reinterpret_cast<const double2 *>(blk(me ? lane : 0, 0));
-        // diagonal block from S (every lane runs the arithmetic, lane j's result is broadcast and stored), then
-        // L_ij = S L_jj^-T for the rows below; returns the new block of this lane in (x00, x01, x10, x11)
+        // Left-looking by 2 x 2 blocks, lane i owns block row i.  Diagonal block from S (every lane runs the arithmetic,
+        // lane j's result is broadcast and stored), then L_ij = S L_jj^-T for the rows below; returns the new block of
+        // this lane in (x00, x01, x10, x11)
         auto finish_column = [&](int j, double sxx, double sxy, double syx, double syy, double &x00, double &x01, double &x10, double &x11) {
             double r1 = fast_rsqrt(sxx);
             double l21 = syx * r1;
@@ -167,50 +173,10 @@ struct QpWarp {
                 o[0] = make_double2(x00, x01); o[1] = make_double2(x10, x11);
             }
         };
-        // Blocked factorisation.  A panel is four block columns (one 8 x 8 tile column).  Inside a panel the columns are
-        // finished left-looking by the lanes that own the block rows (the k loops below start at the panel); once a
-        // panel is complete its rank-8 contribution is subtracted from every trailing tile by the FP64 tensor cores
-        // (two DMMA.8x8x4 per tile, tiles read from and written back to the workspace): 40 DMMAs for 20 robots in place of
-        // 90 sweeps x 16 DFMAs that ran with 12 to 32 of 32 lanes idle.
-        const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;      // fragment coordinates
-        const int NT = (N + 3) >> 2;
-        auto panel_update = [&](int J) {
-            constexpr int TM = max_tiles(PPL);
-            // A fragments of the finished panel, rows of tile I2: lane holds L[8 I2 + g][8 J + 4 c + t], c = 0, 1
-            double af[TM][2];
-            int rowbase[TM];
-#pragma unroll
-            for (int I2 = 1; I2 < TM; I2++) {
-                const int i = 4 * I2 + fgh;
-                rowbase[I2] = 2 * i * (i + 1);
-                const bool ok = I2 > J && I2 < NT && i < N;
-                const double *src = Lb + rowbase[I2] + 16 * J + 4 * (ft >> 1) + 2 * fa + (ft & 1);
-                af[I2][0] = ok ? src[0] : 0.0;
-                af[I2][1] = ok ? src[8] : 0.0;
-            }
-#pragma unroll
-            for (int J2 = 1; J2 < TM; J2++) {
-                if (J2 <= J || J2 >= NT) continue;
-#pragma unroll
-                for (int I2 = 1; I2 < TM; I2++) {
-                    if (I2 < J2 || I2 >= NT) continue;
-                    const int i = 4 * I2 + fgh, k = 4 * J2 + ft;
-                    const bool ok = i < N && k <= i;
-                    double2 *cp = reinterpret_cast<double2 *>(Lb + rowbase[I2] + 4 * k + 2 * fa);
-                    double2 c = ok ? *cp : make_double2(0.0, 0.0);
-                    dmma_8x8x4(c.x, c.y, -af[I2][0], af[J2][0]);
-                    dmma_8x8x4(c.x, c.y, -af[I2][1], af[J2][1]);
-                    if (i == k && fa == 0) c.y = 0.0;       // the element above the diagonal of a diagonal block stays 0
-                    if (ok) *cp = c;
-                }
-            }
-            __syncwarp();
-        };
         int j = 0;
         // two block columns per sweep: one load of this lane's block (i,k) feeds the updates of S_ij and S_i,j+1
         // (16 FMAs per two lane-varying and four broadcast 128-bit loads instead of 8 per two and two)
         for (; j + 1 < N; j += 2) {
-            const int k0 = kTiles ? (j & ~3) : 0;           // first block column of this panel
             double axx = 1.0, axy = 0.0, ayx = 0.0, ayy = 1.0, bxx = 1.0, bxy = 0.0, byx = 0.0, byy = 1.0;
             if (me && lane >= j) {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
@@ -218,7 +184,7 @@ struct QpWarp {
                 const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
                 axx = a0.x; axy = a0.y; ayx = a1.x; ayy = a1.y;
                 if (lane > j) { const double2 b0 = ri[2 * j + 2], b1 = ri[2 * j + 3]; bxx = b0.x; bxy = b0.y; byx = b1.x; byy = b1.y; }
-                for (int k = k0; k < j; k++) {
+                for (int k = 0; k < j; k++) {
                     const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1], q0 = rj1[2 * k], q1 = rj1[2 * k + 1];
                     axx = fma(-i0.x, p0.x, axx); axx = fma(-i0.y, p0.y, axx);
                     axy = fma(-i0.x, p1.x, axy); axy = fma(-i0.y, p1.y, axy);
@@ -243,7 +209,6 @@ struct QpWarp {
             double y00, y01, y10, y11;
             finish_column(j + 1, bxx, bxy, byx, byy, y00, y01, y10, y11);
             __syncwarp();
-            if (kTiles && (j & 3) == 2 && j + 2 < N) panel_update(j >> 2);
         }
         if (j < N) {                                        // odd team size: the last block column on its own
             double sxx = 1.0, sxy = 0.0, syx = 0.0, syy = 1.0;
@@ -251,7 +216,7 @@ struct QpWarp {
                 const double2 *rj = reinterpret_cast<const double2 *>(blk(j, 0));
                 const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1];
                 sxx = a0.x; sxy = a0.y; syx = a1.x; syy = a1.y;
-                for (int k = kTiles ? (j & ~3) : 0; k < j; k++) {
+                for (int k = 0; k < j; k++) {
                     const double2 i0 = ri[2 * k], i1 = ri[2 * k + 1], p0 = rj[2 * k], p1 = rj[2 * k + 1];
                     sxx = fma(-i0.x, p0.x, sxx); sxx = fma(-i0.y, p0.y, sxx);
                     sxy = fma(-i0.x, p1.x, sxy); sxy = fma(-i0.y, p1.y, sxy);
@@ -263,29 +228,109 @@ struct QpWarp {
             finish_column(j, sxx, sxy, syx, syy, x00, x01, x10, x11);
             __syncwarp();
         }
-        // Inverses of the diagonal 8 x 8 tiles of L (the triangular solves below multiply by them instead of running
-        // four dependent 2 x 2 steps per tile): lane (T, c) = (lane / 8, lane % 8) solves L_TT x = e_c by forward
-        // substitution; four tiles per round.  Rows past the matrix (ragged last tile) give zeros.
-        for (int T0 = 0; kTiles && T0 < NT; T0 += 4) {
+    }
+    // Compile-time team size, a multiple of 4: RIGHT-LOOKING factorisation by pairs of block columns (4 matrix columns)
+    // with the trailing updates on the FP64 tensor cores.  Every Schur complement is complete in the workspace when its
+    // turn comes, so (1) every lane reads the 4 x 4 diagonal block of the pair with broadcast loads and factors it
+    // redundantly -- no shuffles, nothing to wait for from another lane; (2) the lane of every later robot turns its own
+    // 2 x 4 strip into L by forward substitution; (3) one DMMA.8x8x4 per trailing 8 x 8 tile subtracts the rank-4
+    // contribution of the pair (tiles are read from and written back to the workspace in the accumulator layout).  55
+    // DMMAs per factorisation of 20 robots replace 90 left-looking sweeps of 16 DFMAs that ran with 12 to 32 of the 32
+    // lanes idle; the inverses of the diagonal 8 x 8 tiles (for solve()) come last.
+    __device__ void factor_tiles()
+    {
+        static_assert(NC % 4 == 0, "the tile path is written for whole 8 x 8 tiles");
+        constexpr int TM = NC / 4;
+        const bool me = lane < N;
+        double2 *ri = reinterpret_cast<double2 *>(blk(me ? lane : 0, 0));
+        const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;      // fragment coordinates
+        int rowbase[TM];
+#pragma unroll
+        for (int I = 0; I < TM; I++) { const int i = 4 * I + fgh; rowbase[I] = 2 * i * (i + 1); }
+        const int fo = 4 * (ft >> 1) + 2 * fa + (ft & 1);   // A fragment: L[8 I + g][4 jp + t] = Lb[rowbase[I] + 8 jp + fo]
+        for (int jp = 0; jp < NC / 2; jp++) {
+            const int j = 2 * jp;
+            // (1) 4 x 4 diagonal block [[s00], [s10 s11], [s20 s21 s22], [s30 s31 s32 s33]] -> its Cholesky factor
+            const double2 *dj = reinterpret_cast<const double2 *>(blk(j, j)), *mj = reinterpret_cast<const double2 *>(blk(j + 1, j)),
+                          *ej = reinterpret_cast<const double2 *>(blk(j + 1, j + 1));
+            const double2 d0 = dj[0], d1 = dj[1], m0 = mj[0], m1 = mj[1], e0 = ej[0], e1 = ej[1];
+            const double r0 = fast_rsqrt(d0.x);
+            const double l10 = d1.x * r0, l20 = m0.x * r0, l30 = m1.x * r0;
+            const double p1 = fma(-l10, l10, d1.y);
+            const double r1 = fast_rsqrt(p1);
+            const double l21 = fma(-l20, l10, m0.y) * r1, l31 = fma(-l30, l10, m1.y) * r1;
+            const double p2 = fma(-l21, l21, fma(-l20, l20, e0.x));
+            const double r2 = fast_rsqrt(p2);
+            const double l32 = fma(-l31, l21, fma(-l30, l20, e1.x)) * r2;
+            const double p3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, e1.y)));
+            const double r3 = fast_rsqrt(p3);
+            __syncwarp();                                   // every lane has read the block before it is overwritten
+            if (lane == j) {
+                double2 *o = reinterpret_cast<double2 *>(blk(j, j));
+                o[0] = make_double2(d0.x * r0, 0.0); o[1] = make_double2(l10, p1 * r1);
+                *reinterpret_cast<double2 *>(invd + 2 * j) = make_double2(r0, r1);
+            } else if (lane == j + 1) {
+                double2 *o = reinterpret_cast<double2 *>(blk(j + 1, j));
+                o[0] = make_double2(l20, l21); o[1] = make_double2(l30, l31);
+                o[2] = make_double2(p2 * r2, 0.0); o[3] = make_double2(l32, p3 * r3);        // block (j + 1, j + 1) follows (j + 1, j)
+                *reinterpret_cast<double2 *>(invd + 2 * j + 2) = make_double2(r2, r3);
+            } else if (me && lane > j + 1) {
+                // (2) rows 2 i, 2 i + 1 of columns 2 j .. 2 j + 3: x L44' = s
+                const double2 a0 = ri[2 * j], a1 = ri[2 * j + 1], b0 = ri[2 * j + 2], b1 = ri[2 * j + 3];
+                const double x0 = a0.x * r0, y0 = a1.x * r0;
+                const double x1 = fma(-x0, l10, a0.y) * r1, y1 = fma(-y0, l10, a1.y) * r1;
+                const double x2 = fma(-x1, l21, fma(-x0, l20, b0.x)) * r2, y2 = fma(-y1, l21, fma(-y0, l20, b1.x)) * r2;
+                const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, b0.y))) * r3, y3 = fma(-y2, l32, fma(-y1, l31, fma(-y0, l30, b1.y))) * r3;
+                ri[2 * j] = make_double2(x0, x1); ri[2 * j + 1] = make_double2(y0, y1);
+                ri[2 * j + 2] = make_double2(x2, x3); ri[2 * j + 3] = make_double2(y2, y3);
+            }
+            __syncwarp();
+            if (jp == NC / 2 - 1) break;
+            // (3) trailing tiles (I2, J2), J2 >= J0.  After the first pair of a tile column that column is still open:
+            // its tiles take part, and only their columns 4 .. 7 (t >= 2) are written back.
+            const int J = jp >> 1, half = jp & 1, J0 = J + half;
+            double af[TM];
+#pragma unroll
+            for (int I = 0; I < TM; I++) af[I] = I >= J0 ? Lb[rowbase[I] + 8 * jp + fo] : 0.0;
+#pragma unroll
+            for (int J2 = 0; J2 < TM; J2++) {
+                if (J2 < J0) continue;
+                const bool open = J2 == J;                  // (then half == 0)
+#pragma unroll
+                for (int I2 = 0; I2 < TM; I2++) {
+                    if (I2 < J2) continue;
+                    const int i = 4 * I2 + fgh, k = 4 * J2 + ft;
+                    const bool ok = k <= i && !(open && ft < 2);
+                    double2 *cp = reinterpret_cast<double2 *>(Lb + rowbase[I2] + 4 * k + 2 * fa);
+                    double2 c = ok ? *cp : make_double2(0.0, 0.0);
+                    dmma_8x8x4(c.x, c.y, -af[I2], af[J2]);
+                    if (i == k && fa == 0) c.y = 0.0;       // the element above the diagonal of a diagonal block stays 0
+                    if (ok) *cp = c;
+                }
+            }
+            __syncwarp();
+        }
+        // Inverses of the diagonal 8 x 8 tiles of L (the triangular solves multiply by them instead of running four
+        // dependent 2 x 2 steps per tile): lane (T, c) = (lane / 8, lane % 8) solves L_TT x = e_c by forward
+        // substitution; four tiles per round.
+        for (int T0 = 0; T0 < TM; T0 += 4) {
             const int T = T0 + (lane >> 3), c = lane & 7;
-            const bool okT = T < NT;
+            const bool okT = T < TM;
             const int Tc = okT ? T : 0;
-            const int nv = okT ? (n - 8 * Tc < 8 ? n - 8 * Tc : 8) : 0;     // rows of this tile inside the matrix
             double x[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const bool okr = r < nv;
                 const int i = 4 * Tc + (r >> 1);
                 // row r of the tile: (L[r][2q], L[r][2q + 1]) = blk(i, 4T + q)[2 (r % 2) ..]
                 const double2 *row = reinterpret_cast<const double2 *>(Lb + 2 * i * (i + 1) + 16 * Tc + 2 * (r & 1));
                 double sum = r == c ? 1.0 : 0.0;
 #pragma unroll
                 for (int q = 0; 2 * q < r; q++) {
-                    const double2 l = okr ? row[2 * q] : make_double2(0.0, 0.0);
+                    const double2 l = row[2 * q];
                     sum = fma(-l.x, x[2 * q], sum);
                     if (2 * q + 1 < r) sum = fma(-l.y, x[2 * q + 1], sum);
                 }
-                x[r] = okr ? sum * invd[8 * Tc + r] : 0.0;
+                x[r] = sum * invd[8 * Tc + r];
             }
             if (okT) {
 #pragma unroll
@@ -307,62 +352,68 @@ struct QpWarp {
         const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;
         const int NT = (N + 3) >> 2;
         const int s0 = 4 * ft, s1 = 16 + 4 * ft;            // lanes holding elements t and 4 + t of a tile in row layout
-        double acc[TM], nb[TM][2];
+        double acc[TM][2];                                  // both accumulators of a tile's DMMAs (equal by construction)
         int rowbase[TM];
 #pragma unroll
         for (int I = 0; I < TM; I++) {
             const int i = 4 * I + fgh;
             rowbase[I] = 2 * i * (i + 1);
-            acc[I] = (I < NT && 8 * I + fg < n) ? b[8 * I + fg] : 0.0;
+            acc[I][0] = acc[I][1] = (I < NT && 8 * I + fg < n) ? b[8 * I + fg] : 0.0;
         }
         // B fragments of a vector held in row layout: lane (g, t) needs elements 4 c + t, c = 0, 1
         auto spread = [&](double v, double &b0, double &b1) { b0 = __shfl_sync(kFull, v, s0); b1 = __shfl_sync(kFull, v, s1); };
+        // "Push" order: as soon as a tile of the solution is known it is applied to every later tile, so the DMMAs
+        // of one step are independent of each other and only two of them sit between consecutive diagonal steps.
+        // The two half products of a diagonal step run in parallel and are added.
 #pragma unroll
-        for (int I = 0; I < TM; I++) {
-            if (I >= NT) continue;
-            double c0 = acc[I], c1 = c0;
-            const bool okr = 8 * I + fg < n;
+        for (int J = 0; J < TM; J++) {
+            if (J >= NT) continue;
+            double t0, t1, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, n0, n1;
+            spread(acc[J][0], t0, t1);
+            const double *inv = Li + 64 * J + 8 * fg + ft;
+            dmma_8x8x4(d0, d1, inv[0], t0);
+            dmma_8x8x4(e0, e1, inv[4], t1);
+            d0 += e0;
+            acc[J][0] = d0;
+            spread(-d0, n0, n1);
 #pragma unroll
-            for (int J = 0; J < TM; J++) {
-                if (J >= I) continue;
+            for (int I = 0; I < TM; I++) {
+                if (I <= J || I >= NT) continue;
+                const bool okr = 8 * I + fg < n;
                 // L[8 I + g][8 J + 4 c + t]
                 const double *src = Lb + rowbase[I] + 16 * J + 4 * (ft >> 1) + 2 * fa + (ft & 1);
-                dmma_8x8x4(c0, c1, okr ? src[0] : 0.0, nb[J][0]);
-                dmma_8x8x4(c0, c1, okr ? src[8] : 0.0, nb[J][1]);
+                dmma_8x8x4(acc[I][0], acc[I][1], okr ? src[0] : 0.0, n0);
+                dmma_8x8x4(acc[I][0], acc[I][1], okr ? src[8] : 0.0, n1);
             }
-            double t0, t1, d0 = 0.0, d1 = 0.0;
-            spread(c0, t0, t1);
-            const double *inv = Li + 64 * I + 8 * fg + ft;
-            dmma_8x8x4(d0, d1, inv[0], t0);
-            dmma_8x8x4(d0, d1, inv[4], t1);
-            acc[I] = d0;
-            spread(-d0, nb[I][0], nb[I][1]);
         }
 #pragma unroll
-        for (int I = TM - 1; I >= 0; I--) {
-            if (I >= NT) continue;
-            double c0 = acc[I], c1 = c0;
+        for (int I = 0; I < TM; I++) acc[I][1] = acc[I][0];
 #pragma unroll
-            for (int J = TM - 1; J >= 0; J--) {
-                if (J <= I || J >= NT) continue;
-                // (L_JI)'[g][4 c + t] = L[8 J + 4 c + t][8 I + g]
-                const int i0 = 4 * J + (ft >> 1), i1 = i0 + 2;
-                const int off = 16 * I + 4 * fgh + 2 * (ft & 1) + fa;
-                dmma_8x8x4(c0, c1, 8 * J + ft < n ? Lb[2 * i0 * (i0 + 1) + off] : 0.0, nb[J][0]);
-                dmma_8x8x4(c0, c1, 8 * J + 4 + ft < n ? Lb[2 * i1 * (i1 + 1) + off] : 0.0, nb[J][1]);
-            }
-            double t0, t1, d0 = 0.0, d1 = 0.0;
-            spread(c0, t0, t1);
-            const double *inv = Li + 64 * I + 8 * ft + fg;      // inv(L_II)'[g][4 c + t] = inv[4 c + t][g]
+        for (int J = TM - 1; J >= 0; J--) {
+            if (J >= NT) continue;
+            double t0, t1, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, n0, n1;
+            spread(acc[J][0], t0, t1);
+            const double *inv = Li + 64 * J + 8 * ft + fg;      // inv(L_JJ)'[g][4 c + t] = inv[4 c + t][g]
             dmma_8x8x4(d0, d1, inv[0], t0);
-            dmma_8x8x4(d0, d1, inv[32], t1);
-            acc[I] = d0;
-            spread(-d0, nb[I][0], nb[I][1]);
+            dmma_8x8x4(e0, e1, inv[32], t1);
+            d0 += e0;
+            acc[J][0] = d0;
+            spread(-d0, n0, n1);
+            // (L_JI)'[g][4 c + t] = L[8 J + 4 c + t][8 I + g], rows 8 J .. of L applied to the earlier tiles I < J
+            const int i0 = 4 * J + (ft >> 1), i1 = i0 + 2;
+            const bool ok0 = 8 * J + ft < n, ok1 = 8 * J + 4 + ft < n;
+            const double *r0 = Lb + 2 * i0 * (i0 + 1) + 4 * fgh + 2 * (ft & 1) + fa, *r1 = Lb + 2 * i1 * (i1 + 1) + 4 * fgh + 2 * (ft & 1) + fa;
+#pragma unroll
+            for (int I = TM - 1; I >= 0; I--) {
+                if (I >= J) continue;
+                dmma_8x8x4(acc[I][0], acc[I][1], ok0 ? r0[16 * I] : 0.0, n0);
+                dmma_8x8x4(acc[I][0], acc[I][1], ok1 ? r1[16 * I] : 0.0, n1);
+            }
         }
         if (ft == 0) {
 #pragma unroll
             for (int I = 0; I < TM; I++)
-                if (I < NT && 8 * I + fg < n) b[8 * I + fg] = acc[I];
+                if (I < NT && 8 * I + fg < n) b[8 * I + fg] = acc[I][0];
         }
         __syncwarp();
     }

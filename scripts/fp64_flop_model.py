@@ -3,7 +3,8 @@
 
     # on the B200 box, ONE GPU (ncu serialises and replays every kernel):
     ncu --metrics smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,\
-smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,gpu__time_duration.sum --clock-control none -k regex:step_ \
+smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sm__inst_executed_pipe_tensor_subpipe_dmma.sum,gpu__time_duration.sum \
+        --clock-control none -k regex:step_ \
         --csv --log-file gpurun_out/fp64_counts.csv python scripts/fp64_flop_model.py collect
     # anywhere:
     python scripts/fp64_flop_model.py fit gpurun_out/fp64_counts.csv gpurun_out/fp64_launches.json profiles/r02_fp64_flop_model.json
@@ -12,7 +13,9 @@ smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,gpu__time_duration.sum --clo
 (sub-steps, QP solves, IPM iterations, env steps): update_frequency 15 / 29 / 45 and robotarium = True, and records
 the statistics-vector delta of every launch (same order as ncu's launch list).  `fit` joins the two, solves the
 least-squares problem per kernel and prints the coefficients to paste into flop_model.COEFFICIENTS.
-flops = dadd + dmul + 2 dfma, thread-level, predicated-on (lanes idling in a diverged warp do not count)."""
+flops = dadd + dmul + 2 dfma, thread-level, predicated-on (lanes idling in a diverged warp do not count), + 512 per warp-level
+DMMA.8x8x4 (the 20-robot kernel's tile updates and tile solves; 8 x 8 x 4 multiply-adds, executed whether or not every column
+of the product is used)."""
 import csv
 import json
 import os
@@ -72,7 +75,7 @@ def fit(csv_path, launches_path, out_path):
     groups = {}
     for l, r in zip(launches, records):
         fl = l["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] + l["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] \
-            + 2.0 * l["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]
+            + 2.0 * l["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"] + 512.0 * l.get("sm__inst_executed_pipe_tensor_subpipe_dmma.sum", 0.0)
         d = r["delta"]
         groups.setdefault((r["scenario"], r["robots"]), []).append(
             ([d["substeps"], d["qp_solves"], d["qp_iterations"], d["env_steps"]], fl, l, r))
@@ -92,6 +95,7 @@ def fit(csv_path, launches_path, out_path):
                           "dadd": i[2]["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"],
                           "dmul": i[2]["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"],
                           "dfma": i[2]["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"],
+                          "dmma_warp": i[2].get("sm__inst_executed_pipe_tensor_subpipe_dmma.sum", 0.0),
                           "flops": i[1], "model_flops": float(np.dot(i[0], co)),
                           "ncu_duration_ns": i[2].get("gpu__time_duration.sum")} for i in items]}
     with open(out_path, "w") as f:

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/lockstep_counts.jsonl
 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; tail -3 gpurun_out/t_all.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-M=smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,gpu__time_duration.sum
+M=smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sm__inst_executed_pipe_tensor_subpipe_dmma.sum,gpu__time_duration.sum
 timeout 600 ncu --metrics $M --clock-control none -k regex:step_ --csv --log-file gpurun_out/fp64_counts.csv python scripts/fp64_flop_model.py collect > gpurun_out/fp64_collect.log 2>&1; tail -1 gpurun_out/fp64_collect.log
 ncu --set full --clock-control none --import-source on -k regex:step_thread -s 8 -c 1 -o gpurun_out/r02_pcp4_final -f python scripts/quick_time.py PredatorCapturePrey 65536 5 > gpurun_out/ncu_pcp4.log 2>&1; tail -1 gpurun_out/ncu_pcp4.log
 ncu --set full --clock-control none --import-source on -k regex:step_thread -s 8 -c 1 -o gpurun_out/r02_wh6_final -f python scripts/quick_time.py Warehouse 262144 5 > gpurun_out/ncu_wh6.log 2>&1; tail -1 gpurun_out/ncu_wh6.log
