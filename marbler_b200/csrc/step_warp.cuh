@@ -248,7 +248,8 @@ struct QpWarp {
 #pragma unroll
         for (int I = 0; I < TM; I++) { const int i = 4 * I + fgh; rowbase[I] = 2 * i * (i + 1); }
         const int fo = 4 * (ft >> 1) + 2 * fa + (ft & 1);   // A fragment: L[8 I + g][4 jp + t] = Lb[rowbase[I] + 8 jp + fo]
-        for (int jp = 0; jp < NC / 2; jp++) {
+#pragma unroll
+        for (int jp = 0; jp < NC / 2; jp++) {               // unrolled: tile ranges, block addresses and most predicates are literals
             const int j = 2 * jp;
             // (1) 4 x 4 diagonal block [[s00], [s10 s11], [s20 s21 s22], [s30 s31 s32 s33]] -> its Cholesky factor
             const double2 *dj = reinterpret_cast<const double2 *>(blk(j, j)), *mj = reinterpret_cast<const double2 *>(blk(j + 1, j)),
