@@ -39,6 +39,11 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// D = A * B (C = 0: the zero register, no accumulator to clear)
+__device__ __forceinline__ void dmma_8x8x4_zero(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0));
+}
 // 8 x 8 tiles (4 robots) per dimension that a team served by PPL pair slots per lane can have
 __host__ __device__ constexpr int max_tiles(int ppl) { return ppl <= 1 ? 2 : ppl <= 2 ? 3 : ppl <= 4 ? 4 : ppl <= 6 ? 5 : ppl <= 8 ? 6 : 8; }
 
@@ -111,13 +116,16 @@ struct QpWarp {
             const double2 *x2 = reinterpret_cast<const double2 *>(xi2);
             const double2 me2 = x2[lane];
             const double *row = y + lane * NS;
-            double sx = 0.0, sy = 0.0;
-            for (int j = 0; j < N; j++) {
-                const double2 o = x2[j];
-                const double t = row[j];
+            double sx = 0.0, sy = 0.0, sx1 = 0.0, sy1 = 0.0;        // even / odd terms: half the dependent depth
+            int j = 0;
+            for (; j + 1 < N; j += 2) {
+                const double2 o = x2[j], o1 = x2[j + 1];
+                const double t = row[j], t1 = row[j + 1];
                 sx = fma(me2.x - o.x, t, sx); sy = fma(me2.y - o.y, t, sy);
+                sx1 = fma(me2.x - o1.x, t1, sx1); sy1 = fma(me2.y - o1.y, t1, sy1);
             }
-            out[2 * lane] -= sx; out[2 * lane + 1] -= sy;
+            if (j < N) { const double2 o = x2[j]; const double t = row[j]; sx = fma(me2.x - o.x, t, sx); sy = fma(me2.y - o.y, t, sy); }
+            out[2 * lane] -= sx + sx1; out[2 * lane + 1] -= sy + sy1;
         }
     }
     // K := 2I + G' diag(w) G as the lower triangle of 2 x 2 blocks (lane i builds block row i)
@@ -369,11 +377,11 @@ struct QpWarp {
 #pragma unroll
         for (int J = 0; J < TM; J++) {
             if (J >= NT) continue;
-            double t0, t1, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, n0, n1;
+            double t0, t1, d0, d1, e0, e1, n0, n1;
             spread(acc[J][0], t0, t1);
             const double *inv = Li + 64 * J + 8 * fg + ft;
-            dmma_8x8x4(d0, d1, inv[0], t0);
-            dmma_8x8x4(e0, e1, inv[4], t1);
+            dmma_8x8x4_zero(d0, d1, inv[0], t0);
+            dmma_8x8x4_zero(e0, e1, inv[4], t1);
             d0 += e0;
             acc[J][0] = d0;
             spread(-d0, n0, n1);
@@ -392,11 +400,11 @@ struct QpWarp {
 #pragma unroll
         for (int J = TM - 1; J >= 0; J--) {
             if (J >= NT) continue;
-            double t0, t1, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, n0, n1;
+            double t0, t1, d0, d1, e0, e1, n0, n1;
             spread(acc[J][0], t0, t1);
             const double *inv = Li + 64 * J + 8 * ft + fg;      // inv(L_JJ)'[g][4 c + t] = inv[4 c + t][g]
-            dmma_8x8x4(d0, d1, inv[0], t0);
-            dmma_8x8x4(e0, e1, inv[32], t1);
+            dmma_8x8x4_zero(d0, d1, inv[0], t0);
+            dmma_8x8x4_zero(e0, e1, inv[32], t1);
             d0 += e0;
             acc[J][0] = d0;
             spread(-d0, n0, n1);

@@ -54,6 +54,45 @@ def test_barrier_qp_matches_restated_cvxopt():
             assert err[conv].max() < 1e-8, (N, kind, err[conv].max())
 
 
+def test_tensor_core_qp_equals_the_block_solver_on_hard_layouts(monkeypatch):
+    """20 robots: the FP64 tensor-core solver (DMMA tile factorisation, inverted diagonal tiles, tile solves) against the
+    2 x 2-block solver of the run-time team sizes on 16,384 random layouts that include what the fixtures have few of:
+    pairs inside the safety radius (gain 1e6, KKT condition ~1e10), near-coincident robots and exactly symmetric rows."""
+    from marbler_b200.vec_env import barrier_qp
+    rng = np.random.RandomState(11)
+    B, N = 16384, 20
+    xi = np.stack([rng.uniform(-1.5, 1.5, (B, N)), rng.uniform(-0.9, 0.9, (B, N))], axis=1)
+    close = rng.rand(B) < 0.5                              # pull a few robots onto their neighbours
+    for b in np.nonzero(close)[0]:
+        k = rng.randint(1, 6)
+        src, dst = rng.randint(0, N, k), rng.randint(0, N, k)
+        ok = src != dst
+        xi[b][:, dst[ok]] = xi[b][:, src[ok]] + rng.uniform(-0.12, 0.12, (2, ok.sum())) * rng.choice([1.0, 0.05], ok.sum())
+    grid = rng.rand(B) < 0.1                               # spawn-grid symmetry: one column, equal spacing
+    xi[grid, 0, :] = -1.4
+    xi[grid, 1, :] = np.linspace(-0.9, 0.9, N)
+    dxi = rng.uniform(-0.3, 0.3, (B, 2, N))
+    d, x = torch.tensor(dxi, device="cuda:0"), torch.tensor(xi, device="cuda:0")
+    for kind in (False, True):
+        u_t, it_t = barrier_qp(d, x, barrier_default=kind)
+        monkeypatch.setenv("MRB_WARP_GENERIC", "1")
+        u_g, it_g = barrier_qp(d, x, barrier_default=kind)
+        monkeypatch.delenv("MRB_WARP_GENERIC")
+        it_t, it_g = it_t.cpu().numpy(), it_g.cpu().numpy()
+        err = np.abs((u_t - u_g).cpu().numpy()).reshape(B, -1).max(axis=1)
+        assert np.isfinite(u_t.cpu().numpy()).all()
+        same = it_t == it_g
+        settled = same & (it_g < 25)                       # equal iteration counts outside cvxopt's limit cycles
+        assert same.mean() > 0.995, (kind, same.mean())
+        # two orderings of the same arithmetic on KKT systems of condition ~1e10: agreement degrades to ~1e-7 on the
+        # worst layouts (north_star bar for QP velocities: 1e-4), and stays at rounding level on the rest
+        q50, q99 = np.percentile(err[settled], [50, 99])
+        assert err[settled].max() < 0.1 * QP_TOL, (kind, err[settled].max())
+        assert q99 < 1e-8 and q50 < 1e-10, (kind, q50, q99)
+        print("tensor-core vs block solver, default=%s: equal iteration counts %.4f, |du| max %.2e  99%% %.2e  median %.2e, mean iterations %.2f" % (
+            kind, same.mean(), err[settled].max(), q99, q50, it_t.mean()))
+
+
 @pytest.mark.parametrize("name", gu.fixture_names())
 def test_step_matches_reference_fixture(name):
     g = gu.Golden(name)
