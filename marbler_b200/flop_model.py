@@ -5,7 +5,8 @@ iterations, env steps):
     flops = a * substeps + b * qp_solves + c * qp_iterations + d * env_steps
 
 The coefficients are FITTED, per kernel, to instruction counts measured with ncu on the B200
-(smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum, flops = dadd + dmul + 2 dfma) over launches of
+(smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum and sm__inst_executed_pipe_tensor_subpipe_dmma.sum,
+flops = dadd + dmul + 2 dfma + 512 dmma) over launches of
 config variants that decorrelate the four counters (update_frequency 15 / 29 / 45, robotarium = True);
 scripts/fp64_flop_model.py collects the data and does the fit, profiles/r02_fp64_flop_model.json holds the raw
 counts, the fit and its residuals.  Thread-level predicated-on counts: lanes idling in a diverged warp do not
@@ -19,9 +20,11 @@ COEFFICIENTS = {
     ("MaterialTransport", 4): (95.8, 1292.9, 869.7, 114.5),
     ("ArcticTransport", 4): (94.5, 1108.8, 892.4, 153.8),
     ("Warehouse", 6): (176.0, 2309.2, 3114.6, 230.2),
-    # one env per warp: the counts include the arithmetic every lane repeats (e.g. the diagonal-block factorisation is
-    # run by all 32 lanes and one result is kept), i.e. executed rather than minimal flops
-    ("PredatorCapturePrey", 20): (1465.4, 68580.1, 84837.2, 22824.4),
+    # one env per warp: the counts include the arithmetic every lane repeats (e.g. the 4 x 4 diagonal blocks of the
+    # factorisation are computed by all 32 lanes) and 512 flops per DMMA.8x8x4 whether or not all eight columns of the
+    # product are used (the tile solves use one): executed rather than minimal flops -- an occupancy figure of the FP64
+    # units, not comparable with the count of the round-1 kernel (84.8 k per iteration, no DMMA)
+    ("PredatorCapturePrey", 20): (1465.4, 103297.1, 143760.2, 22824.4),
 }
 
 
