@@ -3,6 +3,8 @@
 // constraints of the barrier QP are distributed round-robin over the lanes (slot k of lane l is
 // pair l + 32 k); the 2N x 2N KKT matrix and the small vectors live in a per-warp shared-memory
 // workspace.  Same algorithm, constants and reference citations as step_thread.cuh / qp_thread.cuh.
+// With a compile-time team size (20 robots, BASELINE config 5) the Newton system is factored and solved by 8 x 8
+// tiles on the FP64 tensor cores (QpWarp::factor_tiles / solve); run-time team sizes use 2 x 2 blocks on the FP64 pipe.
 #pragma once
 #include <cstdlib>
 
@@ -33,8 +35,9 @@ __device__ __forceinline__ double warp_max(double v)
 }
 // FP64 tensor-core tile product D = A (8 x 4, row) * B (4 x 8, col) + C (8 x 8) = one DMMA.8x8x4 on sm_100a.  Lane
 // (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t + 1].  Measured on the B200
-// (scripts/microbench/dmma.cu, profiles/r02_dmma_microbench.txt): 26 cycles latency, 16 cycles of the FP64 pipe per
-// scheduler -- the flop rate of 8 warp-DFMAs at full lane use -- so it buys instruction slots and lane efficiency, not flops.
+// (scripts/microbench/dmma.cu, profiles/r02_dmma_microbench.txt): 26 cycles latency, one per 16 cycles and scheduler
+// (37 TFLOP/s, and DFMAs issued beside it slow it down) -- the flop rate of 8 warp-DFMAs at full lane use -- so it buys
+// instruction slots and lane efficiency, not flops.
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
