@@ -248,6 +248,14 @@ def test_other_team_sizes_and_options_lockstep(oracle_lib, scenario, overrides):
     _lockstep(oracle_lib, scenario, 1024, 25, overrides=overrides, stall_frac=1e-3)      # measured: none in any of these
 
 
+@pytest.mark.parametrize("predator,capture", [(12, 11), (13, 13)], ids=["N=23", "N=26"])
+def test_large_teams_lockstep(oracle_lib, predator, capture):
+    """The widest instantiations of the warp kernel (8 and 16 pair slots per lane; an odd team size takes the
+    single-column tail of the factorisation): 23 and 26 robots on the 5 x 6 spawn grid, K = 3 nearest neighbours."""
+    _lockstep(oracle_lib, "PredatorCapturePrey", 256, 12, stall_frac=1e-2,
+              overrides=dict(predator=predator, capture=capture, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
+
+
 PCP20 = dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)
 
 
