@@ -422,6 +422,7 @@ struct QpWarp {
                 dmma_8x8x4(acc[I][0], acc[I][1], ok1 ? r1[16 * I] : 0.0, n1);
             }
         }
+        __syncwarp();                                       // the four lanes of a group all read b[8 I + g] above
         if (ft == 0) {
 #pragma unroll
             for (int I = 0; I < TM; I++)
