@@ -768,11 +768,17 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
         if (c.num_neighbors >= N - 1) {
             for (int b = 0; b < N; b++) if (b != lane) put(b);
         } else {
+            // the rounded norms once (row `lane` of an idle pair matrix), then one compare-and-select pass per neighbour
+            double *drow = qp.Wm + lane * qp.NS;
+            for (int b = 0; b < N; b++) {
+                const double dx = spx[b] - px, dy = spy[b] - py;
+                drow[b] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            }
             uint32_t used = 1u << lane;
             for (int kk = 0; kk < c.num_neighbors; kk++) {
                 int best = -1; double bdist = 0.0;
                 for (int b = 0; b < N; b++) {
-                    const double dx = spx[b] - px, dy = spy[b] - py, dd = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    const double dd = drow[b];
                     if (!((used >> b) & 1) && (best < 0 || dd < bdist)) { best = b; bdist = dd; }
                 }
                 used |= 1u << best;
