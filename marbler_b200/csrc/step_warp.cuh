@@ -47,8 +47,6 @@ __device__ __forceinline__ void dmma_8x8x4_zero(double &d0, double &d1, double a
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0));
 }
-// 8 x 8 tiles (4 robots) per dimension that a team served by PPL pair slots per lane can have
-__host__ __device__ constexpr int max_tiles(int ppl) { return ppl <= 1 ? 2 : ppl <= 2 ? 3 : ppl <= 4 ? 4 : ppl <= 6 ? 5 : ppl <= 8 ? 6 : 8; }
 
 // Per-warp shared-memory workspace (doubles).  The Cholesky factor is stored as the lower triangle of
 // N x N blocks of 2 x 2 (block (i,k), k <= i, at 4 * (i (i + 1) / 2 + k): [xx, xy, yx, yy] = rows 2i, 2i+1 x
@@ -358,19 +356,22 @@ struct QpWarp {
     // robots instead of twenty 2 x 2 steps with two shuffle broadcasts each.
     __device__ void solve(double *b) const
     {
-        if constexpr (!kTiles) { solve_rows(b); return; }
+        if constexpr (kTiles) solve_tiles(b);
+        else solve_rows(b);
+    }
+    __device__ void solve_tiles(double *b) const
+    {
         __syncwarp();
-        constexpr int TM = max_tiles(PPL);
+        constexpr int TM = NC / 4;                           // whole tiles (static_assert in factor_tiles)
         const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;
-        const int NT = (N + 3) >> 2;
         const int s0 = 4 * ft, s1 = 16 + 4 * ft;            // lanes holding elements t and 4 + t of a tile in row layout
-        double acc[TM][2];                                  // both accumulators of a tile's DMMAs (equal by construction)
-        int rowbase[TM];
+        double acc[TM > 0 ? TM : 1][2];                     // both accumulators of a tile's DMMAs (equal by construction)
+        int rowbase[TM > 0 ? TM : 1];
 #pragma unroll
         for (int I = 0; I < TM; I++) {
             const int i = 4 * I + fgh;
             rowbase[I] = 2 * i * (i + 1);
-            acc[I][0] = acc[I][1] = (I < NT && 8 * I + fg < n) ? b[8 * I + fg] : 0.0;
+            acc[I][0] = acc[I][1] = b[8 * I + fg];
         }
         // B fragments of a vector held in row layout: lane (g, t) needs elements 4 c + t, c = 0, 1
         auto spread = [&](double v, double &b0, double &b1) { b0 = __shfl_sync(kFull, v, s0); b1 = __shfl_sync(kFull, v, s1); };
@@ -379,7 +380,6 @@ struct QpWarp {
         // The two half products of a diagonal step run in parallel and are added.
 #pragma unroll
         for (int J = 0; J < TM; J++) {
-            if (J >= NT) continue;
             double t0, t1, d0, d1, e0, e1, n0, n1;
             spread(acc[J][0], t0, t1);
             const double *inv = Li + 64 * J + 8 * fg + ft;
@@ -389,20 +389,17 @@ struct QpWarp {
             acc[J][0] = d0;
             spread(-d0, n0, n1);
 #pragma unroll
-            for (int I = 0; I < TM; I++) {
-                if (I <= J || I >= NT) continue;
-                const bool okr = 8 * I + fg < n;
+            for (int I = J + 1; I < TM; I++) {
                 // L[8 I + g][8 J + 4 c + t]
                 const double *src = Lb + rowbase[I] + 16 * J + 4 * (ft >> 1) + 2 * fa + (ft & 1);
-                dmma_8x8x4(acc[I][0], acc[I][1], okr ? src[0] : 0.0, n0);
-                dmma_8x8x4(acc[I][0], acc[I][1], okr ? src[8] : 0.0, n1);
+                dmma_8x8x4(acc[I][0], acc[I][1], src[0], n0);
+                dmma_8x8x4(acc[I][0], acc[I][1], src[8], n1);
             }
         }
 #pragma unroll
         for (int I = 0; I < TM; I++) acc[I][1] = acc[I][0];
 #pragma unroll
         for (int J = TM - 1; J >= 0; J--) {
-            if (J >= NT) continue;
             double t0, t1, d0, d1, e0, e1, n0, n1;
             spread(acc[J][0], t0, t1);
             const double *inv = Li + 64 * J + 8 * ft + fg;      // inv(L_JJ)'[g][4 c + t] = inv[4 c + t][g]
@@ -413,20 +410,17 @@ struct QpWarp {
             spread(-d0, n0, n1);
             // (L_JI)'[g][4 c + t] = L[8 J + 4 c + t][8 I + g], rows 8 J .. of L applied to the earlier tiles I < J
             const int i0 = 4 * J + (ft >> 1), i1 = i0 + 2;
-            const bool ok0 = 8 * J + ft < n, ok1 = 8 * J + 4 + ft < n;
             const double *r0 = Lb + 2 * i0 * (i0 + 1) + 4 * fgh + 2 * (ft & 1) + fa, *r1 = Lb + 2 * i1 * (i1 + 1) + 4 * fgh + 2 * (ft & 1) + fa;
 #pragma unroll
-            for (int I = TM - 1; I >= 0; I--) {
-                if (I >= J) continue;
-                dmma_8x8x4(acc[I][0], acc[I][1], ok0 ? r0[16 * I] : 0.0, n0);
-                dmma_8x8x4(acc[I][0], acc[I][1], ok1 ? r1[16 * I] : 0.0, n1);
+            for (int I = J - 1; I >= 0; I--) {
+                dmma_8x8x4(acc[I][0], acc[I][1], r0[16 * I], n0);
+                dmma_8x8x4(acc[I][0], acc[I][1], r1[16 * I], n1);
             }
         }
         __syncwarp();                                       // the four lanes of a group all read b[8 I + g] above
         if (ft == 0) {
 #pragma unroll
-            for (int I = 0; I < TM; I++)
-                if (I < NT && 8 * I + fg < n) b[8 * I + fg] = acc[I][0];
+            for (int I = 0; I < TM; I++) b[8 * I + fg] = acc[I][0];
         }
         __syncwarp();
     }
