@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launchers.h"
 
 namespace mrb {
 
@@ -56,12 +57,19 @@ __device__ __forceinline__ void dmma_8x8x4_zero(double &d0, double &d1, double a
 // (1.6x the conflict-free wavefronts and five integer instructions per element before); the pair's owner writes both
 // mirror entries.  The pair directions a_ij = 2 (x_i - x_j) are not stored: they are differences of the doubled
 // positions (exact), read as broadcast 128-bit loads.
-__host__ __device__ inline int pair_row_stride(int N) { return N | 1; }
-__host__ __device__ inline size_t warp_workspace_doubles(int N)
+__host__ __device__ constexpr int pair_row_stride(int N) { return N | 1; }
+__host__ __device__ constexpr size_t warp_workspace_doubles(int N)
 {
-    const size_t n = 2 * (size_t)N;
-    const size_t d = 2 * (size_t)N * (N + 1) + 6 * n + 2 * (size_t)N * pair_row_stride(N);
-    return ((d + 1) & ~(size_t)1) + 64 * (((size_t)N + 3) / 4);          // + the inverses of the diagonal 8 x 8 tiles of L
+    // factor blocks + six n-vectors + two pair matrices (even) + the inverses of the diagonal 8 x 8 tiles of L
+    return ((2 * (size_t)N * (N + 1) + 12 * (size_t)N + 2 * (size_t)N * pair_row_stride(N) + 1) & ~(size_t)1) + 64 * (((size_t)N + 3) / 4);
+}
+// Compile-time team sizes (the tensor-core solver): exact number of pair slots per lane, and as many warps in ONE CTA per SM
+// as the workspace (227 KB) and the register file (168 registers at 12 warps) allow
+__host__ __device__ constexpr int team_ppl(int N) { return (N * (N - 1) / 2 + 31) / 32; }
+__host__ __device__ constexpr int team_warps(int N)
+{
+    const int fit = (int)((227 * 1024) / (warp_workspace_doubles(N) * sizeof(double)));
+    return fit < 12 ? fit : 12;
 }
 
 // NC: compile-time team size (0 = generic).  The tensor-core paths (DMMA panel updates of the factor, tile solves) are
@@ -644,7 +652,7 @@ struct QpWarp {
 // 14 k-instruction body roughly in step and share the instruction fetches (21.8 vs 22.5 ms per 32,768 envs); the generic
 // path keeps 4-warp CTAs because the workspace of a 32-robot team would not fit twelve times.
 template <int SCN, int PPL, int NC = 0, int WPB = kWarpsPerBlock>
-__global__ void __launch_bounds__(WPB * 32, WPB == kWarpsPerBlock ? MRB_WARP_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(WPB * 32, NC == 0 ? MRB_WARP_MIN_BLOCKS : 1)
 step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
     extern __shared__ __align__(16) double smem[];
@@ -972,7 +980,7 @@ inline int pairs_per_lane(int N) { return (N * (N - 1) / 2 + 31) / 32; }
 template <int SCN, int PPL, int NC = 0>
 inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions, cudaStream_t s)
 {
-    constexpr int WPB = NC == 20 ? 12 : kWarpsPerBlock;
+    constexpr int WPB = NC != 0 ? team_warps(NC) : kWarpsPerBlock;
     const size_t smem = warp_workspace_doubles(p.cfg.num_robots) * sizeof(double) * WPB;
     cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL, NC, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
@@ -986,8 +994,13 @@ inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cud
 {
     // ArcticTransport (exactly 4 robots, per-terrain step sizes, grid observations) exists on the thread kernel only
     if (SCN == MRB_ARCTIC) return cudaErrorNotSupported;
+    // team sizes with a kernel of their own (kern_team_*.cu): the tensor-core solver
+    if (!std::getenv("MRB_WARP_GENERIC")) {
+        bool handled = false;
+        const cudaError_t st = launch_step_team(SCN, p, actions, s, &handled);
+        if (handled) return st;
+    }
     const int ppl = pairs_per_lane(p.cfg.num_robots);
-    if (SCN == MRB_PCP && p.cfg.num_robots == 20 && !std::getenv("MRB_WARP_GENERIC")) return launch_step_warp_ppl<SCN, 6, 20>(p, actions, s);
     if (ppl <= 1) return launch_step_warp_ppl<SCN, 1>(p, actions, s);
     if (ppl <= 2) return launch_step_warp_ppl<SCN, 2>(p, actions, s);
     if (ppl <= 4) return launch_step_warp_ppl<SCN, 4>(p, actions, s);
@@ -1026,8 +1039,12 @@ inline cudaError_t launch_qp_warp_ppl(int N, int bd, int64_t B, const double *dx
 }
 inline cudaError_t launch_qp_warp(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
 {
+    if (!std::getenv("MRB_WARP_GENERIC")) {             // team sizes with the tensor-core solver (kern_team_*.cu)
+        bool handled = false;
+        const cudaError_t st = launch_qp_team(N, bd, B, dxi, xi, u, iters, s, &handled);
+        if (handled) return st;
+    }
     const int ppl = pairs_per_lane(N);
-    if (N == 20 && !std::getenv("MRB_WARP_GENERIC")) return launch_qp_warp_ppl<6, 20>(N, bd, B, dxi, xi, u, iters, s);   // the tensor-core solver
     if (ppl <= 1) return launch_qp_warp_ppl<1>(N, bd, B, dxi, xi, u, iters, s);
     if (ppl <= 2) return launch_qp_warp_ppl<2>(N, bd, B, dxi, xi, u, iters, s);
     if (ppl <= 4) return launch_qp_warp_ppl<4>(N, bd, B, dxi, xi, u, iters, s);

@@ -250,10 +250,27 @@ def test_other_team_sizes_and_options_lockstep(oracle_lib, scenario, overrides):
 
 @pytest.mark.parametrize("predator,capture", [(12, 11), (13, 13)], ids=["N=23", "N=26"])
 def test_large_teams_lockstep(oracle_lib, predator, capture):
-    """The widest instantiations of the warp kernel (8 and 16 pair slots per lane; an odd team size takes the
-    single-column tail of the factorisation): 23 and 26 robots on the 5 x 6 spawn grid, K = 3 nearest neighbours."""
+    """The widest instantiations of the run-time team size kernel (8 and 16 pair slots per lane; an odd team size takes
+    the single-column tail of the factorisation): 23 and 26 robots on the 5 x 6 spawn grid, K = 3 nearest neighbours."""
     _lockstep(oracle_lib, "PredatorCapturePrey", 256, 12, stall_frac=1e-2,
               overrides=dict(predator=predator, capture=capture, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
+
+
+TENSOR_TEAMS = [("PredatorCapturePrey", dict(predator=6, capture=6, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),
+                ("PredatorCapturePrey", dict(predator=8, capture=8, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=15)),
+                ("PredatorCapturePrey", dict(predator=12, capture=12, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),
+                ("PredatorCapturePrey", dict(predator=14, capture=14, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),
+                ("Warehouse", dict(n_agents=8, num_neighbors=7)),
+                ("Simple", dict(n_agents=8, ROBOT_INIT_RIGHT_THRESH=0.1)),
+                ("Simple", dict(n_agents=12, ROBOT_INIT_RIGHT_THRESH=0.1)),
+                ("Simple", dict(n_agents=16, ROBOT_INIT_RIGHT_THRESH=0.1))]
+
+
+@pytest.mark.parametrize("scenario,overrides", TENSOR_TEAMS, ids=["PCP-12", "PCP-16", "PCP-24", "PCP-28", "Warehouse-8", "Simple-8", "Simple-12", "Simple-16"])
+def test_tensor_core_team_sizes_lockstep(oracle_lib, scenario, overrides):
+    """Every (scenario, team size) that has a kernel of its own with the FP64 tensor-core solver (csrc/kern_team_*.cu;
+    PCP-8 is in TEAM_CASES, PCP-20 in test_lockstep_20_robots), against the C oracle."""
+    _lockstep(oracle_lib, scenario, 512, 14, overrides=overrides, stall_frac=1e-2)
 
 
 PCP20 = dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)
