@@ -72,13 +72,16 @@ __host__ __device__ constexpr int team_warps(int N)
     return fit < 12 ? fit : 12;
 }
 
-// NC: compile-time team size (0 = generic).  The tensor-core paths (DMMA panel updates of the factor, tile solves) are
-// compiled for NC != 0 only: with the team size known their tile loops and predicates fold away; with a run-time team
-// size the same code spills and is slower than the 2 x 2-block code it replaces (measured, 20 robots: 39.7 vs 28.5 ms).
-template <int PPL, int NC = 0>
+// NC: compile-time size of the Newton system in robots, a multiple of 4 (0 = run-time team size, 2 x 2-block code).  The
+// tensor-core paths (DMMA tile updates of the factor, tile solves) need it at compile time: their tile loops and predicates
+// fold away; with run-time tile counts the same code spills and is slower than the 2 x 2-block code (measured, 20 robots:
+// 39.7 vs 28.5 ms).  EXACT: the team has exactly NC robots (loops over robots fold too); otherwise N <= NC robots at run
+// time and robots N .. NC - 1 are phantoms without constraints: their rows of K are 2I, their entries of every vector 0.
+template <int PPL, int NC = 0, bool EXACT = true>
 struct QpWarp {
     static constexpr bool kTiles = NC != 0;
     int N, n, m, lane;
+    int NP;                                               // robots the workspace is laid out for (NC, or N)
     int NS;                                               // row stride of the pair matrices
     double *Lb, *invd, *vx, *vq, *vrx, *vdx, *xi2, *Wm, *Ym, *Li;
     int pi[PPL], pj[PPL];
@@ -87,11 +90,18 @@ struct QpWarp {
 
     __device__ QpWarp(int N_, double *ws, int lane_) : N(N_), n(2 * N_), m(N_ * (N_ - 1) / 2), lane(lane_)
     {
-        Lb = ws; invd = Lb + 2 * (size_t)N * (N + 1); vx = invd + n; vq = vx + n; vrx = vq + n; vdx = vrx + n;
-        NS = pair_row_stride(N);
-        xi2 = vdx + n;                                    // (2 x_i, 2 y_i), interleaved
-        Wm = xi2 + n; Ym = Wm + (size_t)N * NS;           // Ym holds z or the right-hand-side multipliers (never live together)
-        Li = ws + (warp_workspace_doubles(N) - 64 * (((size_t)N + 3) / 4));      // dense row-major 8 x 8 per diagonal tile
+        NP = kTiles ? NC : N;
+        const int np = 2 * NP;
+        Lb = ws; invd = Lb + 2 * (size_t)NP * (NP + 1); vx = invd + np; vq = vx + np; vrx = vq + np; vdx = vrx + np;
+        NS = pair_row_stride(NP);
+        xi2 = vdx + np;                                   // (2 x_i, 2 y_i), interleaved
+        Wm = xi2 + np; Ym = Wm + (size_t)NP * NS;         // Ym holds z or the right-hand-side multipliers (never live together)
+        Li = ws + (warp_workspace_doubles(NP) - 64 * (((size_t)NP + 3) / 4));    // dense row-major 8 x 8 per diagonal tile
+        if (kTiles && !EXACT) {                           // phantom robots: no weights, zero vectors (never written afterwards)
+            for (int k = lane; k < 2 * NP * NS; k += 32) Wm[k] = 0.0;
+            for (int k = 2 * N + lane; k < np; k += 32) { vx[k] = 0.0; vq[k] = 0.0; vrx[k] = 0.0; vdx[k] = 0.0; xi2[k] = 0.0; }
+            __syncwarp();
+        }
 #pragma unroll
         for (int k = 0; k < PPL; k++) {                   // decode my pair slots once
             const int c = lane + 32 * k;
@@ -141,12 +151,13 @@ struct QpWarp {
     __device__ __forceinline__ void assemble()
     {
         __syncwarp();
-        if (lane < N) {
+        const int NA = kTiles ? NC : N;                     // the tile path also builds the (2I) rows of phantom robots
+        if (lane < NA) {
             double dxx = 2.0, dxy = 0.0, dyy = 2.0;
             const double2 *x2 = reinterpret_cast<const double2 *>(xi2);
             const double2 me2 = x2[lane];
             const double *wrow = Wm + lane * NS;
-            for (int j = 0; j < N; j++) {
+            for (int j = 0; j < NA; j++) {
                 const double2 xo = x2[j];
                 const double w = wrow[j], a = me2.x - xo.x, b = me2.y - xo.y;    // w_ii = 0
                 const double wa = w * a, wb = w * b;
@@ -258,7 +269,7 @@ struct QpWarp {
     {
         static_assert(NC % 4 == 0, "the tile path is written for whole 8 x 8 tiles");
         constexpr int TM = NC / 4;
-        const bool me = lane < N;
+        const bool me = lane < NC;
         double2 *ri = reinterpret_cast<double2 *>(blk(me ? lane : 0, 0));
         const int fg = lane >> 2, ft = lane & 3, fgh = fg >> 1, fa = fg & 1;      // fragment coordinates
         int rowbase[TM];
@@ -651,7 +662,7 @@ struct QpWarp {
 // WPB: warps (= envs) per CTA.  The 20-robot instantiation runs its 12 resident warps as ONE CTA: they then execute the
 // 14 k-instruction body roughly in step and share the instruction fetches (21.8 vs 22.5 ms per 32,768 envs); the generic
 // path keeps 4-warp CTAs because the workspace of a 32-robot team would not fit twelve times.
-template <int SCN, int PPL, int NC = 0, int WPB = kWarpsPerBlock>
+template <int SCN, int PPL, int NC = 0, int WPB = kWarpsPerBlock, bool EXACT = true>
 __global__ void __launch_bounds__(WPB * 32, NC == 0 ? MRB_WARP_MIN_BLOCKS : 1)
 step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ actions)
 {
@@ -660,13 +671,13 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
     const int64_t env = p.env_lo + (int64_t)blockIdx.x * WPB + wib;
     if (env >= p.env_hi) return;
     const mrb_config &c = p.cfg;
-    const int N = NC ? NC : c.num_robots;
+    const int N = (NC && EXACT) ? NC : c.num_robots;
     const int64_t S = p.B;
     double *sf = p.buf.state_f64 + env;
     int32_t *si = p.buf.state_i32 + env;
     int32_t *sci = si + kCommonRowsI32 * S;
     double *scf = sf + (5 * N + 1) * S;
-    QpWarp<PPL, NC> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    QpWarp<PPL, NC, EXACT> qp(N, smem + (size_t)wib * warp_workspace_doubles(NC ? NC : N), lane);
     const bool me = lane < N;
 
     double px = 0, py = 0, th = 0, qx = 0, qy = 0;
@@ -977,15 +988,15 @@ step_warp_kernel(const __grid_constant__ Params p, const int32_t *__restrict__ a
 
 inline int pairs_per_lane(int N) { return (N * (N - 1) / 2 + 31) / 32; }
 
-template <int SCN, int PPL, int NC = 0>
+template <int SCN, int PPL, int NC = 0, bool EXACT = true>
 inline cudaError_t launch_step_warp_ppl(const Params &p, const int32_t *actions, cudaStream_t s)
 {
     constexpr int WPB = NC != 0 ? team_warps(NC) : kWarpsPerBlock;
-    const size_t smem = warp_workspace_doubles(p.cfg.num_robots) * sizeof(double) * WPB;
-    cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL, NC, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = warp_workspace_doubles(NC ? NC : p.cfg.num_robots) * sizeof(double) * WPB;
+    cudaError_t st = cudaFuncSetAttribute(step_warp_kernel<SCN, PPL, NC, WPB, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
     const unsigned grid = (unsigned)((p.env_hi - p.env_lo + WPB - 1) / WPB);
-    step_warp_kernel<SCN, PPL, NC, WPB><<<grid, WPB * 32, smem, s>>>(p, actions);
+    step_warp_kernel<SCN, PPL, NC, WPB, EXACT><<<grid, WPB * 32, smem, s>>>(p, actions);
     return cudaSuccess;
 }
 
@@ -1010,7 +1021,7 @@ inline cudaError_t launch_step_warp(const Params &p, const int32_t *actions, cud
 }
 
 // ---- barrier QP alone, one problem per warp
-template <int PPL, int NC = 0>
+template <int PPL, int NC = 0, bool EXACT = true>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MRB_WARP_MIN_BLOCKS)
 qp_warp_kernel(int N_, int64_t B, int barrier_default, const double *__restrict__ dxi, const double *__restrict__ xi,
                double *__restrict__ u, int32_t *__restrict__ iters)
@@ -1019,8 +1030,8 @@ qp_warp_kernel(int N_, int64_t B, int barrier_default, const double *__restrict_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (e >= B) return;
-    const int N = NC ? NC : N_;
-    QpWarp<PPL, NC> qp(N, smem + (size_t)wib * warp_workspace_doubles(N), lane);
+    const int N = (NC && EXACT) ? NC : N_;
+    QpWarp<PPL, NC, EXACT> qp(N, smem + (size_t)wib * warp_workspace_doubles(NC ? NC : N), lane);
     double xx = 0, xy = 0, ux = 0, uy = 0;
     if (lane < N) { xx = xi[lane * B + e]; xy = xi[(N + lane) * B + e]; ux = dxi[lane * B + e]; uy = dxi[(N + lane) * B + e]; }
     const int it = qp.run(xx, xy, ux, uy, barrier_default != 0);
@@ -1028,13 +1039,13 @@ qp_warp_kernel(int N_, int64_t B, int barrier_default, const double *__restrict_
     if (iters && lane == 0) iters[e] = it;
 }
 
-template <int PPL, int NC = 0>
+template <int PPL, int NC = 0, bool EXACT = true>
 inline cudaError_t launch_qp_warp_ppl(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)
 {
-    const size_t smem = warp_workspace_doubles(N) * sizeof(double) * kWarpsPerBlock;
-    cudaError_t st = cudaFuncSetAttribute(qp_warp_kernel<PPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = warp_workspace_doubles(NC ? NC : N) * sizeof(double) * kWarpsPerBlock;
+    cudaError_t st = cudaFuncSetAttribute(qp_warp_kernel<PPL, NC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
-    qp_warp_kernel<PPL, NC><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem, s>>>(N, B, bd, dxi, xi, u, iters);
+    qp_warp_kernel<PPL, NC, EXACT><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem, s>>>(N, B, bd, dxi, xi, u, iters);
     return cudaSuccess;
 }
 inline cudaError_t launch_qp_warp(int N, int bd, int64_t B, const double *dxi, const double *xi, double *u, int32_t *iters, cudaStream_t s)

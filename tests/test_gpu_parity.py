@@ -260,16 +260,20 @@ TENSOR_TEAMS = [("PredatorCapturePrey", dict(predator=6, capture=6, ROBOT_INIT_R
                 ("PredatorCapturePrey", dict(predator=8, capture=8, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=15)),
                 ("PredatorCapturePrey", dict(predator=12, capture=12, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),
                 ("PredatorCapturePrey", dict(predator=14, capture=14, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),
+                ("PredatorCapturePrey", dict(predator=15, capture=14, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3)),   # 29 on 32
+                ("PredatorCapturePrey", dict(predator=9, capture=9, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=17)),    # 18 on 20
+                ("Warehouse", dict(n_agents=11, num_neighbors=10)),                                                    # 11 on 12
                 ("Warehouse", dict(n_agents=8, num_neighbors=7)),
                 ("Simple", dict(n_agents=8, ROBOT_INIT_RIGHT_THRESH=0.1)),
                 ("Simple", dict(n_agents=12, ROBOT_INIT_RIGHT_THRESH=0.1)),
                 ("Simple", dict(n_agents=16, ROBOT_INIT_RIGHT_THRESH=0.1))]
 
 
-@pytest.mark.parametrize("scenario,overrides", TENSOR_TEAMS, ids=["PCP-12", "PCP-16", "PCP-24", "PCP-28", "Warehouse-8", "Simple-8", "Simple-12", "Simple-16"])
+@pytest.mark.parametrize("scenario,overrides", TENSOR_TEAMS, ids=["PCP-12", "PCP-16", "PCP-24", "PCP-28", "PCP-29on32", "PCP-18on20", "Warehouse-11on12", "Warehouse-8", "Simple-8", "Simple-12", "Simple-16"])
 def test_tensor_core_team_sizes_lockstep(oracle_lib, scenario, overrides):
-    """Every (scenario, team size) that has a kernel of its own with the FP64 tensor-core solver (csrc/kern_team_*.cu;
-    PCP-8 is in TEAM_CASES, PCP-20 in test_lockstep_20_robots), against the C oracle."""
+    """Every (scenario, size) that has a kernel of its own with the FP64 tensor-core solver (csrc/kern_team_*.cu), with
+    the team size folded into the code and padded with phantom robots (PCP-8, PCP-10 on 12 ... are in TEAM_CASES and
+    test_large_teams_lockstep, PCP-20 in test_lockstep_20_robots), against the C oracle."""
     _lockstep(oracle_lib, scenario, 512, 14, overrides=overrides, stall_frac=1e-2)
 
 
