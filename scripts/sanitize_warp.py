@@ -18,12 +18,18 @@ def run(B, over, steps=2):
     torch.cuda.synchronize()
     print("ok", B, over)
 
-run(24, dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
+run(24, dict(predator=10, capture=10, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))          # 20 robots, folded
+run(16, dict(predator=4, capture=5, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))            # 9 on 12, padded
+run(8, dict(predator=12, capture=11, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3), steps=1)  # 23 on 24
+run(5, dict(predator=15, capture=14, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3), steps=1)  # 29 on 32
+os.environ["MRB_WARP_GENERIC"] = "1"                                                          # run-time team size kernels
 run(16, dict(predator=4, capture=5, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3))
 run(8, dict(predator=12, capture=11, ROBOT_INIT_RIGHT_THRESH=0.1, num_neighbors=3), steps=1)
+del os.environ["MRB_WARP_GENERIC"]
 g = torch.Generator(device="cuda:0").manual_seed(2)
 xi = torch.rand((16, 2, 20), generator=g, device="cuda:0", dtype=torch.float64) * 2 - 1
 dxi = torch.rand((16, 2, 20), generator=g, device="cuda:0", dtype=torch.float64) * 0.4 - 0.2
 u, it = barrier_qp(dxi, xi)
+u2, it2 = barrier_qp(dxi[:, :, :18].contiguous(), xi[:, :, :18].contiguous())              # 18 on 20, padded
 torch.cuda.synchronize()
-print("ok qp", it.cpu().numpy().tolist())
+print("ok qp", it.cpu().numpy().tolist(), it2.cpu().numpy().tolist())
