@@ -24,7 +24,7 @@ COEFFICIENTS = {
     # factorisation are computed by all 32 lanes) and 512 flops per DMMA.8x8x4 whether or not all eight columns of the
     # product are used (the tile solves use one): executed rather than minimal flops -- an occupancy figure of the FP64
     # units, not comparable with the count of the round-1 kernel (84.8 k per iteration, no DMMA)
-    ("PredatorCapturePrey", 20): (1465.4, 103297.1, 143760.2, 22824.4),
+    ("PredatorCapturePrey", 20): (1465.3, 103290.5, 143760.6, 8656.3),
 }
 
 
