@@ -66,10 +66,15 @@ __host__ __device__ constexpr size_t warp_workspace_doubles(int N)
 // Compile-time team sizes (the tensor-core solver): exact number of pair slots per lane, and as many warps in ONE CTA per SM
 // as the workspace (227 KB) and the register file (168 registers at 12 warps) allow
 __host__ __device__ constexpr int team_ppl(int N) { return (N * (N - 1) / 2 + 31) / 32; }
+// (register file: 168 registers at 12 warps; small teams need fewer -- measured, 65,536 envs: 8 robots 6.54 ms at 12 warps,
+// 5.91 at 16, 5.78 at 20; 12 robots 11.30 / 10.99 / 10.99; 16 robots 17.85 / 17.21 / 18.18)
+#ifndef MRB_TEAM_WARPS_CAP
+#define MRB_TEAM_WARPS_CAP(N) ((N) <= 8 ? 20 : (N) <= 16 ? 16 : 12)
+#endif
 __host__ __device__ constexpr int team_warps(int N)
 {
     const int fit = (int)((227 * 1024) / (warp_workspace_doubles(N) * sizeof(double)));
-    return fit < 12 ? fit : 12;
+    return fit < MRB_TEAM_WARPS_CAP(N) ? fit : MRB_TEAM_WARPS_CAP(N);
 }
 
 // NC: compile-time size of the Newton system in robots, a multiple of 4 (0 = run-time team size, 2 x 2-block code).  The
