@@ -177,3 +177,29 @@ def test_spawn_grid_division_trick_is_exact():
         inv = (65536 + yr - 1) // yr
         for cell in range(64):
             assert (cell * inv) >> 16 == cell // yr, (cell, yr)
+
+
+def test_every_team_kernel_is_dispatched():
+    """csrc/kern_team_<scenario><size>.cu (one kernel per scenario and size of the Newton system, FP64 tensor-core solver)
+    and the dispatch table csrc/kern_teams.cu are maintained by hand: every unit must be reachable, every case must exist,
+    sizes are multiples of four, and PredatorCapturePrey units carry the QP-alone kernel mrb_barrier_qp uses."""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "marbler_b200", "csrc")
+    table = open(os.path.join(csrc, "kern_teams.cu")).read()
+    units = sorted(glob.glob(os.path.join(csrc, "kern_team_*.cu")))
+    assert len(units) >= 12
+    seen = set()
+    for u in units:
+        src = open(u).read()
+        tag = re.search(r"#define MRB_TEAM_TAG (\w+)", src).group(1)
+        n = int(re.search(r"#define MRB_TEAM_N (\d+)", src).group(1))
+        scn = re.search(r"#define MRB_TEAM_SCN (\w+)", src).group(1)
+        assert n % 4 == 0 and 8 <= n <= 32, u
+        assert os.path.basename(u) == "kern_team_%s%d.cu" % (tag, n)
+        assert re.search(r"if \(scenario == %s\) switch \(size\) \{[^}]*case %d: return launch_step_team_%s_%d\(" % (scn, n, tag, n), table), u
+        if "MRB_TEAM_WITH_QP" in src:
+            assert scn == "MRB_PCP" and "case %d: return launch_qp_team_n_%d(" % (n, n) in table, u
+        seen.add((tag, n))
+    for tag, n in re.findall(r"return launch_step_team_(\w+)_(\d+)\(", table):
+        assert (tag, int(n)) in seen, (tag, n)
