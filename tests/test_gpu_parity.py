@@ -93,6 +93,32 @@ def test_tensor_core_qp_equals_the_block_solver_on_hard_layouts(monkeypatch):
             kind, same.mean(), err[settled].max(), q99, q50, it_t.mean()))
 
 
+def test_every_team_size_matches_the_block_solver(monkeypatch):
+    """mrb_barrier_qp for every team size of 7..32 robots: the kernel with the compile-time size of the Newton system
+    (FP64 tensor cores; N rounded up to a multiple of four, phantom robots when it is not one) against the run-time team
+    size kernel (2 x 2 blocks on the FP64 pipe) on 512 random layouts each, a third of them with close pairs."""
+    from marbler_b200.vec_env import barrier_qp
+    rng = np.random.RandomState(5)
+    B = 512
+    for N in range(7, 33):
+        xi = np.stack([rng.uniform(-1.5, 1.5, (B, N)), rng.uniform(-0.9, 0.9, (B, N))], axis=1)
+        for b in range(0, B, 3):
+            a, c = rng.choice(N, 2, replace=False)
+            xi[b][:, c] = xi[b][:, a] + rng.uniform(-0.15, 0.15, 2)
+        dxi = rng.uniform(-0.3, 0.3, (B, 2, N))
+        d, x = torch.tensor(dxi, device="cuda:0"), torch.tensor(xi, device="cuda:0")
+        u_t, it_t = barrier_qp(d, x)
+        monkeypatch.setenv("MRB_WARP_GENERIC", "1")
+        u_g, it_g = barrier_qp(d, x)
+        monkeypatch.delenv("MRB_WARP_GENERIC")
+        it_t, it_g = it_t.cpu().numpy(), it_g.cpu().numpy()
+        same = it_t == it_g
+        err = np.abs((u_t - u_g).cpu().numpy()).reshape(B, -1).max(axis=1)
+        assert same.mean() >= 0.99, (N, same.mean())
+        assert err[same & (it_g < 25)].max() < 0.1 * QP_TOL, (N, err[same & (it_g < 25)].max())
+        assert np.median(err[same]) < 1e-10, (N, np.median(err[same]))
+
+
 @pytest.mark.parametrize("name", gu.fixture_names())
 def test_step_matches_reference_fixture(name):
     g = gu.Golden(name)
