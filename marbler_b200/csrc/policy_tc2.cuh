@@ -40,7 +40,18 @@ constexpr int kStageWarps = 8, kEpiWarps = MRB_TC2_EPI_WARPS;    // kEpiWarps / 
 constexpr int kColGroups = kEpiWarps / 4;                  // ... and split the 64 units of a pass between them
 constexpr int kUnitsPerWarp = kHalf / kColGroups;
 constexpr int kTileStride = 20;                            // floats per row of an epilogue exchange tile (16 + 4 pad)
-constexpr int kThreads2 = (kEpiWarps + 2 + kStageWarps) * 32;     // 576
+// Warp layout by warpgroups of four (setmaxnreg moves registers between WHOLE warpgroups): epilogue warps 0 .. 7, then one
+// warpgroup holding the MMA issuer, the weight loader and two idle warps, then the eight staging warps.  The kernel starts
+// with 96 registers per thread (640 threads = 61,440 registers, and setmaxnreg only redistributes what the CTA was launched
+// with: asking for more blocks forever); the middle warpgroup drops to 40 and the staging warps to 88, which lets the
+// epilogue warps rise to 128 (8 x 4096 + 4 x 1280 + 8 x 2816 = 60,416).
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kStageBase = kEpiWarps + 4;
+constexpr int kThreads2 = (kStageBase + kStageWarps) * 32;        // 640
+#ifndef MRB_TC2_SETMAXNREG
+#define MRB_TC2_SETMAXNREG 1
+#endif
+template <int R> __device__ __forceinline__ void reg_inc() { if (MRB_TC2_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { if (MRB_TC2_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 constexpr int kMaxA = 8;                                  // fc2 runs on the CUDA cores of the epilogue warps
 
 struct Params2 {
@@ -186,6 +197,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
 
     if (warp < kEpiWarps) {
         // ------------------------------------------------------------------------------------------ epilogue
+        reg_inc<128>();
         const int quarter = warp & 3, cq = warp >> 2;       // TMEM lane quarter (rows 32 quarter ..); which kUnitsPerWarp units of a pass
         const int row = 32 * quarter + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(32 * quarter) << 16);
@@ -330,7 +342,9 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
             }
             epi_sync();
         }
-    } else if (warp == kEpiWarps) {
+    } else if (warp < kStageBase) {
+        reg_dec<40>();                                       // the whole warpgroup: issuer, loader, two idle warps
+        if (warp == kMmaWarp) {
         // ------------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc(kHalf);
@@ -365,7 +379,7 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                 tc_commit(act_free + 8 * b);                // both passes have read x and h of this buffer
             }
         }
-    } else if (warp == kEpiWarps + 1) {
+        } else if (warp == kLoadWarp) {
         // ------------------------------------------------------------------------------------------ weight loader
         if (lane == 0) {
             const uint8_t *img0 = p.img + (size_t)(p.non_shared ? ((int)blockIdx.x % N) : 0) * p.set_bytes;
@@ -383,9 +397,11 @@ policy_act_tc2_kernel(const Params2 p, const float *__restrict__ obs, float *hid
                 }
             }
         }
+        }
     } else {
         // ------------------------------------------------------------------------------------------ staging + fc1
-        const int sw = warp - (kEpiWarps + 2);               // this warp stages rows 16 sw .. 16 sw + 15 of every tile
+        reg_dec<88>();
+        const int sw = warp - kStageBase;                    // this warp stages rows 16 sw .. 16 sw + 15 of every tile
         const int g = lane >> 2, tq = lane & 3;              // mma.sync fragment coordinates
         const int KS = w1_stride(Dp), nk = Dp >> 4;
         mbar_wait_sleep(head_full, 0);
