@@ -16,10 +16,13 @@
 //   mma       1 thread per tile two half passes of 64 hidden units; a pass is 6 slabs x 8 tcgen05.mma (M 128, N 64,
 //                      K 16) into one 256-column half of TMEM: r -> [0,64), z -> [64,128), W_in x -> [128,192),
 //                      W_hn h -> [192,256); tcgen05.commit releases slabs, activation buffers and TMEM halves
-//   epilogue  4 warps  thread t = tile row t = TMEM lane t: tcgen05.ld the four gate accumulators, gates on the SFU,
-//                      h' -> global, fc2 partial sums on the CUDA cores (A <= 32 actions), argmax after the second
-//                      pass.  While it works on one TMEM half the MMAs of the next pass fill the other.
+//   epilogue  8 warps  two per TMEM lane quarter, each with half of a pass's 64 units; thread t of a quarter = tile row =
+//                      TMEM lane: tcgen05.ld the four gate accumulators, gates on the SFU, h' -> global through a
+//                      per-warp transpose tile, fc2 partial sums on the CUDA cores (A <= 8 actions), argmax after the
+//                      second pass.  While it works on one TMEM half the MMAs of the next pass fill the other.
 //
+// The warps are laid out by warpgroups of four -- epilogue 0 .. 7 | issuer, loader, two idle | staging 12 .. 19 -- so that
+// setmaxnreg can move registers from the issuer / loader group (40) and the staging warps (88) to the epilogue (128).
 // Every wait on an mbarrier is bounded and traps instead of hanging the GPU.
 #pragma once
 #include "policy_tc.cuh"
